@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on CPU.
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    python tests/golden/make_golden.py
+
+What it imports from the reference (nothing is copied into this repo):
+  * xpoint.models.vmamba_src.csms6s.selective_scan_torch           (csms6s.py:25-68)
+  * selective_scan_ref, exec'd from the kernel test file's source   (test_selective_scan.py:168-234)
+  * xpoint.models.vmamba_src.csm_triton.cross_scan_fwd / cross_merge_fwd / *1b1*  (csm_triton.py:22-179)
+  * xpoint.models.vmamba_src.VMamba.SS2D / VSSM                     (VMamba.py:1107, :1243)
+  * xpoint.models.XPoint.XPoint                                     (XPoint.py:27)
+  * xpoint.utils.utils.box_nms / interpolate_descriptors            (utils.py:148, :229)
+  * xpoint.utils.matching.get_matches / NNMatcher                   (matching.py:4, :38)
+Import shims for timm / fvcore / yacs live in tests/golden/_shims (those packages are not in
+the image).  The only behavioural patch is the one SURVEY 0.8 documents: `cross_scan_fn`
+wraps its call in torch.cuda.device(x.device), which raises on CPU, so VMamba's
+cross_scan_fn / cross_merge_fn are rebound to the reference's own CrossScanF / CrossMergeF.
+"""
+import ast
+import os
+import sys
+import tempfile
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("XPOINT_REFERENCE", "/root/reference")
+sys.path.insert(0, os.path.join(HERE, "_shims"))
+sys.path.insert(0, REF)
+warnings.filterwarnings("ignore")
+
+import xpoint.models as xmodels  # noqa: E402
+import xpoint.utils as xutils  # noqa: E402
+from xpoint.models.vmamba_src import VMamba as RV  # noqa: E402
+from xpoint.models.vmamba_src import csm_triton as RC  # noqa: E402
+from xpoint.models.vmamba_src import csms6s as RS  # noqa: E402
+
+torch.set_num_threads(8)
+
+
+def load_selective_scan_ref():
+    path = os.path.join(REF, "xpoint/models/vmamba_src/kernels/selective_scan/test_selective_scan.py")
+    src = open(path).read()
+    tree = ast.parse(src)
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name == "selective_scan_ref":
+            code = ast.get_source_segment(src, node)
+            ns = {}
+            import torch.nn.functional as F
+            from einops import rearrange, repeat
+            ns.update(torch=torch, F=F, rearrange=rearrange, repeat=repeat)
+            exec(code, ns)
+            return ns["selective_scan_ref"]
+    raise RuntimeError("selective_scan_ref not found")
+
+
+selective_scan_ref = load_selective_scan_ref()
+
+
+def save(name, **arrs):
+    out = {}
+    for k, v in arrs.items():
+        if isinstance(v, torch.Tensor):
+            v = v.detach().float().cpu().numpy() if v.is_floating_point() else v.detach().cpu().numpy()
+        out[k] = np.asarray(v)
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {name}.npz  {os.path.getsize(path)/1024:.1f} KiB")
+
+
+# ------------------------------------------------------------------------------ selective scan
+def scan_inputs(seed, Bt, KD, K, N, L, KD1=None, dtype=torch.float32, three_d=False):
+    """Input distributions of test_selective_scan.py:414-444."""
+    g = torch.Generator().manual_seed(seed)
+    KD1 = KD1 or KD
+    A = -0.5 * torch.rand(KD, N, generator=g)
+    shape = (Bt, N, L) if three_d else (Bt, K, N, L)
+    B = torch.randn(*shape, generator=g).to(dtype)
+    C = torch.randn(*shape, generator=g).to(dtype)
+    D = torch.randn(KD, generator=g)
+    z = torch.randn(Bt, KD, L, generator=g).to(dtype)
+    bias = 0.5 * torch.rand(KD1, generator=g)
+    u = torch.randn(Bt, KD, L, generator=g).to(dtype)
+    delta = (0.5 * torch.rand(Bt, KD1, L, generator=g)).to(dtype)
+    return u, delta, A, B, C, D, z, bias
+
+
+def gen_scan():
+    # XPoint-style grouped call through the importable API (csms6s.py:112 -> selective_scan_torch)
+    for name, (Bt, KD, K, N, L) in dict(scan_n16_k4=(2, 32, 4, 16, 300), scan_n1_k4=(2, 24, 4, 1, 257),
+                                        scan_n8_k2=(1, 12, 2, 8, 64)).items():
+        u, delta, A, B, C, D, z, bias = scan_inputs(0, Bt, KD, K, N, L)
+        out = RS.selective_scan_fn(u, delta, A, B, C, D, bias, True, True, backend="torch")
+        out_t = RS.selective_scan_torch(u, delta, A, B, C, D, bias, True, True)
+        out_r, last = selective_scan_ref(u, delta, A, B, C, D, None, bias, True, return_last_state=True)
+        assert torch.equal(out, out_t)
+        print(name, "selective_scan_torch vs selective_scan_ref max|diff| =", (out_t - out_r).abs().max().item())
+        save(name, u=u, delta=delta, A=A, B=B, C=C, D=D, delta_bias=bias, out=out_t, out_ref=out_r, last_state=last,
+             delta_softplus=1)
+    # mamba-style extras: z gate + last state, no softplus, no bias, no D  (test_selective_scan.py:168-234)
+    u, delta, A, B, C, D, z, bias = scan_inputs(1, 2, 16, 2, 8, 130)
+    out, last = selective_scan_ref(u, delta, A, B, C, None, z, None, False, return_last_state=True)
+    save("scan_z_last", u=u, delta=delta, A=A, B=B, C=C, z=z, out=out, last_state=last, delta_softplus=0)
+    # delta groups: dim1 != dim, reference repeats delta rows (test_selective_scan.py:446-450)
+    u, delta, A, B, C, D, z, bias = scan_inputs(2, 2, 24, 2, 4, 96, KD1=6)
+    delta_rep = delta.unsqueeze(2).repeat(1, 1, 4, 1).contiguous().flatten(1, 2)
+    bias_rep = bias.unsqueeze(1).repeat(1, 4).view(-1)
+    out, last = selective_scan_ref(u, delta_rep, A, B, C, D, None, bias_rep, True, return_last_state=True)
+    save("scan_dgroups", u=u, delta=delta, A=A, B=B, C=C, D=D, delta_bias=bias, out=out, last_state=last,
+         delta_softplus=1)
+    # 3-D B/C (single group)
+    u, delta, A, B, C, D, z, bias = scan_inputs(3, 2, 8, 1, 4, 70, three_d=True)
+    out, last = selective_scan_ref(u, delta, A, B, C, D, z, bias, True, return_last_state=True)
+    save("scan_3d", u=u, delta=delta, A=A, B=B, C=C, D=D, z=z, delta_bias=bias, out=out, last_state=last,
+         delta_softplus=1)
+    # 16-bit inputs: both sides get the same pre-rounded tensors; oflex=True -> fp32 out (csms6s.py:68)
+    for tag, dt in (("bf16", torch.bfloat16), ("fp16", torch.float16)):
+        u, delta, A, B, C, D, z, bias = scan_inputs(4, 2, 16, 4, 16, 200, dtype=dt)
+        out = RS.selective_scan_torch(u, delta, A, B, C, D, bias, True, True)
+        out_in = RS.selective_scan_torch(u, delta, A, B, C, D, bias, True, False)
+        assert out.dtype == torch.float32 and out_in.dtype == dt
+        save("scan_" + tag, u=u, delta=delta, A=A, B=B, C=C, D=D, delta_bias=bias, out=out, out_indtype=out_in,
+             delta_softplus=1)
+
+
+# ------------------------------------------------------------------------------ cross scan/merge
+def gen_cross():
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 3, 5, 7, generator=g)
+    x4 = torch.randn(2, 4, 3, 5, 7, generator=g)
+    ys = torch.randn(2, 4, 3, 5, 7, generator=g)
+    arrs = dict(x=x, x4=x4, ys=ys)
+    for s in (0, 1, 2):
+        arrs[f"scan_s{s}"] = RC.cross_scan_fwd(x, True, True, s)
+        arrs[f"scan_s{s}_cl"] = RC.cross_scan_fwd(x.permute(0, 2, 3, 1).contiguous(), False, False, s)
+        arrs[f"scan_s{s}_cf2cl"] = RC.cross_scan_fwd(x, True, False, s)
+        arrs[f"merge_s{s}"] = RC.cross_merge_fwd(ys, True, True, s)
+        arrs[f"merge_s{s}_cl"] = RC.cross_merge_fwd(ys.permute(0, 3, 4, 1, 2).contiguous(), False, False, s)
+        arrs[f"scan1b1_s{s}"] = RC.cross_scan1b1_fwd(x4, True, True, s)
+        arrs[f"merge1b1_s{s}"] = RC.cross_merge1b1_fwd(ys, True, True, s)
+    # the autograd Function wrappers return (B,4,C,L) / (B,C,L) like the functional forms
+    arrs["F_scan"] = RC.CrossScanF.apply(x, True, True, False, 0)
+    arrs["F_merge"] = RC.CrossMergeF.apply(ys, True, True, False, 0)
+    save("cross", **arrs)
+
+
+# ------------------------------------------------------------------------------ SS2D block
+def patch_cross_for_cpu():
+    RV.cross_scan_fn = lambda x, in_channel_first=True, out_channel_first=True, one_by_one=False, scans=0, force_torch=False: \
+        RC.CrossScanF.apply(x, in_channel_first, out_channel_first, one_by_one, scans)
+    RV.cross_merge_fn = lambda y, in_channel_first=True, out_channel_first=True, one_by_one=False, scans=0, force_torch=False: \
+        RC.CrossMergeF.apply(y, in_channel_first, out_channel_first, one_by_one, scans)
+
+
+def gen_ss2d():
+    patch_cross_for_cpu()
+    for name, kw in dict(
+        ss2d_v0=dict(d_model=16, d_state=4, ssm_ratio=2.0, forward_type="v0"),
+        ss2d_v05_noz=dict(d_model=16, d_state=1, ssm_ratio=1.0, forward_type="v05_noz", conv_bias=False),
+        ss2d_v05=dict(d_model=16, d_state=2, ssm_ratio=2.0, forward_type="v05"),
+    ).items():
+        torch.manual_seed(0)
+        m = RV.SS2D(**kw).eval()
+        with torch.no_grad():
+            # make A / D / norm non-trivial so the test does not pass on initialisation structure
+            m.A_logs.copy_(torch.log(0.5 * torch.rand_like(m.A_logs) + 0.05))
+            m.Ds.copy_(torch.randn_like(m.Ds))
+            m.out_norm.weight.copy_(1 + 0.1 * torch.randn_like(m.out_norm.weight))
+            m.out_norm.bias.copy_(0.1 * torch.randn_like(m.out_norm.bias))
+            x = torch.randn(2, 6, 9, 16)
+            y = m(x)
+        arrs = {"sd." + k: v for k, v in m.state_dict().items()}
+        save(name, x=x, y=y, **arrs)
+
+
+# ------------------------------------------------------------------------------ heads + tail
+def gen_tail():
+    g = torch.Generator().manual_seed(0)
+    logits = 3.0 * torch.randn(2, 65, 6, 8, generator=g)
+    prob = torch.nn.PixelShuffle(8)(torch.nn.Softmax2d()(logits)[:, :-1])  # XPoint.py:356-357
+    draw = torch.randn(2, 256, 6, 8, generator=g)
+    dnorm = torch.nn.functional.normalize(draw, p=2, dim=1)  # XPoint.py:366
+    save("heads", logits=logits, prob=prob, desc_raw=draw, desc=dnorm)
+
+    p1 = torch.rand(96, 120, generator=g) ** 6
+    pb = torch.rand(3, 1, 64, 80, generator=g) ** 6
+    arrs = dict(prob=p1, prob_batched=pb)
+    arrs["nms8"] = xutils.box_nms(p1, 8, 0.015)
+    arrs["nms4"] = xutils.box_nms(p1, 4, 0.015)
+    arrs["nms8_top50"] = xutils.box_nms(p1, 8, 0.015, keep_top_k=50)
+    arrs["nms8_iou03"] = xutils.box_nms(p1, 8, 0.015, iou=0.3)
+    arrs["nms8_batched_top40"] = xutils.box_nms(pb, 8, 0.015, keep_top_k=40, on_cpu=True)
+    arrs["nms8_batched"] = xutils.box_nms(pb, 8, 0.015)
+    kp = torch.nonzero(arrs["nms8"] > 0.015)  # evaluation.py:281-282
+    arrs["kp8"] = kp
+    desc_low = torch.nn.functional.normalize(torch.randn(256, 12, 15, generator=g), p=2, dim=0)
+    arrs["desc_low"] = desc_low
+    arrs["desc_kp"] = xutils.interpolate_descriptors(kp, desc_low, 96, 120)
+    save("tail", **arrs)
+
+
+def gen_match():
+    seed = 0
+    while True:
+        g = torch.Generator().manual_seed(seed)
+        d1 = torch.nn.functional.normalize(torch.randn(300, 256, generator=g), dim=1)
+        # second set: half noisy copies of d1 rows (so many mutual matches), half random
+        perm = torch.randperm(300, generator=g)[:140]
+        d2a = torch.nn.functional.normalize(d1[perm] + 0.08 * torch.randn(140, 256, generator=g), dim=1)
+        d2b = torch.nn.functional.normalize(torch.randn(140, 256, generator=g), dim=1)
+        d2 = torch.cat([d2a, d2b])[torch.randperm(280, generator=g)]
+        dm = torch.cdist(d1.double(), d2.double())
+        s1 = dm.sort(1).values
+        s2 = dm.sort(0).values
+        gap = min((s1[:, 1] - s1[:, 0]).min().item(), (s2[1] - s2[0]).min().item())
+        if gap > 1e-5:
+            break
+        seed += 1
+    n1, n2 = d1.numpy(), d2.numpy()
+    m = xutils.get_matches(n1, n2, "bfmatcher", False, crossCheck=True)  # matching.py:7,34
+    bf = np.array([(x.queryIdx, x.trainIdx) for x in m], dtype=np.int32)
+    bfd = np.array([x.distance for x in m], dtype=np.float32)
+    m2 = xutils.get_matches(n1, n2, "nnmatcher", False, threshold=10.0)  # matching.py:38-75
+    nn_ = np.array([(x.queryIdx, x.trainIdx) for x in m2], dtype=np.int32)
+    nnd = np.array([x.distance for x in m2], dtype=np.float32)
+    print("matches: bf", len(bf), "nn", len(nn_), "min gap", gap, "seed", seed)
+    save("match", d1=d1, d2=d2, bf_pairs=bf, bf_dist=bfd, nn_pairs=nn_, nn_dist=nnd, min_gap=gap)
+
+
+# ------------------------------------------------------------------------------ whole model (config 1, tiny dims)
+TINY = dict(
+    E=dict(DEPTHS=[1, 1, 1, 1], DOWNSAMPLE="v3", EMBED_DIM=16, MLP_RATIO=4.0, PATCHEMBED="v2", SSM_CONV=3,
+           SSM_CONV_BIAS=False, SSM_DT_RANK="auto", SSM_D_STATE=1, SSM_FORWARDTYPE="v05_noz", SSM_RATIO=1.0),
+    V=dict(DEPTHS=[1, 1, 2, 1], DOWNSAMPLE="v1", EMBED_DIM=16, MLP_RATIO=0.0, PATCHEMBED="v1", SSM_CONV=3,
+           SSM_CONV_BIAS=True, SSM_DT_RANK="auto", SSM_D_STATE=4, SSM_FORWARDTYPE="v0", SSM_RATIO=2.0,
+           SSM_INIT="v0", NORM_LAYER="ln"),
+)
+
+
+def gen_model():
+    import yaml
+    patch_cross_for_cpu()
+    for tag, vssm in TINY.items():
+        with tempfile.TemporaryDirectory() as td:
+            ypath = os.path.join(td, "vssm_tiny.yaml")
+            with open(ypath, "w") as f:
+                yaml.safe_dump({"MODEL": {"TYPE": "vssm", "NAME": "tiny", "DROP_PATH_RATE": 0.2, "VSSM": vssm}}, f)
+            cfg = dict(
+                multispectral=False, descriptor_head=True, descriptor_size=256, normalize_descriptors=True,
+                final_batchnorm=True, reflection_pad=True, bn_first=False, mixed_precision=False, takes_pair=True,
+                homography_regression_head=dict(check=False, type="RegNet"),
+                use_attention=dict(check=True, type="VMamba", height=64, width=96,
+                                   pretrained=dict(check=True, yaml_file=ypath), model_parameters={}),
+            )
+            torch.manual_seed(0)
+            net = xmodels.XPoint(cfg).eval()
+        with torch.no_grad():
+            # BatchNorm running stats / SSM params away from their init values
+            for mod in net.modules():
+                if isinstance(mod, torch.nn.BatchNorm2d):
+                    mod.running_mean.normal_(0, 0.1)
+                    mod.running_var.uniform_(0.5, 1.5)
+                    mod.weight.normal_(1.0, 0.1)
+                    mod.bias.normal_(0, 0.1)
+            for n_, p in net.named_parameters():
+                if n_.endswith("A_logs"):
+                    p.copy_(torch.log(0.5 * torch.rand_like(p) + 0.05))
+                if n_.endswith("Ds"):
+                    p.normal_(1.0, 0.3)
+            g = torch.Generator().manual_seed(1)
+            data = {"optical": {"image": torch.rand(2, 1, 64, 96, generator=g)},
+                    "thermal": {"image": torch.rand(2, 1, 64, 96, generator=g)}}
+            po, pt, hm = net(data)
+        assert hm is None and po["logits"] is None
+        arrs = {"sd." + k: v for k, v in net.state_dict().items()}
+        save("xpoint_tiny_" + tag, img_optical=data["optical"]["image"], img_thermal=data["thermal"]["image"],
+             prob_optical=po["prob"], desc_optical=po["desc"], enc_optical=po["encoder_output"],
+             prob_thermal=pt["prob"], desc_thermal=pt["desc"], enc_thermal=pt["encoder_output"], **arrs)
+        print(tag, "params", sum(p.numel() for p in net.parameters()))
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["scan", "cross", "ss2d", "tail", "match", "model"]
+    for w in which:
+        globals()["gen_" + w]()

@@ -1,0 +1,188 @@
+/*
+ * xpoint_b200.h -- C ABI of the B200-native (sm_100a) XPoint inference hot path.
+ *
+ * This is the drop-in boundary: every entry point takes plain device pointers, sizes,
+ * element strides, dtype enums and a CUDA stream; there are no torch / C++ types in any
+ * signature.  The library never allocates device memory, never synchronises the stream
+ * and keeps no global state except a thread-local error string.  All functions return
+ * XP_OK (0) or a negative xp_status; xp_last_error() gives the text.
+ *
+ * Each entry point names the reference interface (file:line in canyagmur/XPoint) it
+ * replaces; INTEGRATION.md shows the reference-side ctypes binding for each.
+ */
+#ifndef XPOINT_B200_H_
+#define XPOINT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XP_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define XP_API __attribute__((visibility("default")))
+#else
+#define XP_API
+#endif
+
+typedef enum {
+    XP_OK = 0,
+    XP_ERR_INVALID_ARG = -1,   /* shape / stride / dtype / null-pointer violation (reference: TORCH_CHECK) */
+    XP_ERR_UNSUPPORTED = -2,   /* valid in the reference, not implemented here (e.g. backward)            */
+    XP_ERR_CUDA = -3,          /* a CUDA runtime / launch error; text in xp_last_error()                   */
+    XP_ERR_WORKSPACE = -4      /* caller-provided workspace too small                                      */
+} xp_status;
+
+typedef enum { XP_F32 = 0, XP_F16 = 1, XP_BF16 = 2 } xp_dtype;
+
+typedef void* xp_stream_t; /* cudaStream_t */
+
+/* -- library ------------------------------------------------------------------------- */
+XP_API int xp_abi_version(void);
+XP_API const char* xp_last_error(void);              /* thread-local, valid until the next failing call */
+/* 0 when the current CUDA device can run this library (compute capability 10.x). */
+XP_API int xp_check_device(void);
+
+/* -- a1/a2: selective scan forward ----------------------------------------------------
+ * Replaces selective_scan_cuda_oflex.fwd  (kernels/selective_scan/csrc/selective_scan/
+ * cusoflex/selective_scan_oflex.cpp:143-231, kernel selective_scan_fwd_kernel_oflex.cuh:67-212)
+ * behind selective_scan_fn (csms6s.py:112-126), plus the mamba_ssm-style extras exercised by
+ * the kernel tests (z gate, last state: test_selective_scan.py:168-234).
+ *
+ *   delta' = softplus(delta + delta_bias)            (softplus optional; threshold 20)
+ *   h_l    = exp(delta'_l * A) * h_{l-1} + delta'_l * B_l * u_l ,   h_{-1} = 0
+ *   out_l  = sum_n C_l[n] * h_l[n] + D * u_l ;   out_l *= silu(z_l)   (z optional)
+ *
+ * u, out, z : (batch, dim, seqlen)            delta : (batch, delta_dim, seqlen), dim % delta_dim == 0
+ * A : (dim, dstate) fp32 contiguous           B, C  : (batch, groups, dstate, seqlen), dim % groups == 0
+ * D : (dim) fp32 or NULL                      delta_bias : (delta_dim) fp32 or NULL
+ * last_state : (batch, dim, dstate) fp32 contiguous or NULL.
+ * u/delta/B/C/z share in_dtype; out has out_dtype (XP_F32, or == in_dtype).  All strides are in
+ * ELEMENTS; the seqlen stride of every tensor must be 1 (same rule as selective_scan_oflex.cpp:170-176).
+ * dstate <= 256.  State and accumulation are always fp32.
+ */
+typedef struct {
+    const void* u;
+    const void* delta;
+    const float* A;
+    const void* B;
+    const void* C;
+    const float* D;          /* nullable */
+    const void* z;           /* nullable */
+    const float* delta_bias; /* nullable */
+    void* out;
+    float* last_state;       /* nullable */
+    int64_t batch, dim, delta_dim, groups, dstate, seqlen;
+    int64_t u_batch_stride, u_dim_stride;
+    int64_t delta_batch_stride, delta_dim_stride;
+    int64_t B_batch_stride, B_group_stride, B_state_stride;
+    int64_t C_batch_stride, C_group_stride, C_state_stride;
+    int64_t z_batch_stride, z_dim_stride;
+    int64_t out_batch_stride, out_dim_stride;
+    int32_t in_dtype;        /* xp_dtype */
+    int32_t out_dtype;       /* xp_dtype */
+    int32_t delta_softplus;  /* bool */
+    int32_t force_generic;   /* debug/testing: 1 = always take the shape-generic kernel */
+} xp_scan_args;
+
+XP_API int xp_selective_scan_fwd(const xp_scan_args* args, xp_stream_t stream);
+
+/* The reference extension also exports bwd (selective_scan_oflex.cpp:233-355).  This library is
+ * inference-only: the symbol exists so a binding can resolve it, and always returns
+ * XP_ERR_UNSUPPORTED. */
+XP_API int xp_selective_scan_bwd(void);
+
+/* -- a3/a4: CrossScan / CrossMerge ----------------------------------------------------
+ * Replace cross_scan_fn / cross_merge_fn and the CrossScanF / CrossMergeF (+Triton) forward
+ * passes (csm_triton.py:22-179, 182-273, 278-517).
+ *   scans 0: l0=h*W+w, l1=w*H+h, l2=L-1-l0, l3=L-1-l1 ; 1: four copies ; 2: two forward + two flipped.
+ * x : channel-first (B,C,H,W) or channel-last (B,H,W,C); with one_by_one (B,4,C,H,W) / (B,H,W,4,C).
+ * xs: channel-first (B,4,C,L) or channel-last (B,L,4,C).
+ * merge: ys as xs above (viewed (B,4,C,H,W) / (B,H,W,4,C)); y channel-first (B,C,L) or channel-last
+ * (B,L,C); with one_by_one y is (B,4,C,L) / (B,L,4,C) and nothing is summed.
+ * Merge sums in fp32 with the torch path's association (y0 + y2') + (y1' + y3') and writes dtype.
+ */
+XP_API int xp_cross_scan(const void* x, void* xs, int64_t B, int64_t C, int64_t H, int64_t W, int32_t dtype,
+                  int32_t in_channel_first, int32_t out_channel_first, int32_t one_by_one, int32_t scans,
+                  xp_stream_t stream);
+XP_API int xp_cross_merge(const void* ys, void* y, int64_t B, int64_t C, int64_t H, int64_t W, int32_t dtype,
+                   int32_t in_channel_first, int32_t out_channel_first, int32_t one_by_one, int32_t scans,
+                   xp_stream_t stream);
+
+/* -- a4+a5 tail: CrossMerge (+) out_norm LayerNorm (+) z gate, one pass ------------------
+ * Replaces cross_merge_fn -> transpose -> out_norm [-> y * z]   (VMamba.py:632-646 and :364-372).
+ * ys : (B, 4, C, L) scan outputs in scan order, fp32 or 16-bit.   gamma/beta : (C) fp32.
+ * zact : (B, L, C) already-activated gate (SiLU(z)) in out dtype, or NULL.
+ * out  : (B, L, C) i.e. (B,H,W,C) channel-last, out_dtype.   eps: LayerNorm epsilon (1e-5).
+ * workspace: xp_merge_norm_gate_workspace_bytes(B, C, H, W) bytes (the merged fp32 activations).
+ */
+XP_API int64_t xp_merge_norm_gate_workspace_bytes(int64_t B, int64_t C, int64_t H, int64_t W);
+XP_API int xp_merge_norm_gate(const void* ys, const float* gamma, const float* beta, const void* zact, void* out,
+                       int64_t B, int64_t C, int64_t H, int64_t W, int32_t ys_dtype, int32_t out_dtype, float eps,
+                       void* workspace, int64_t workspace_bytes, xp_stream_t stream);
+
+/* -- a6: detector post ----------------------------------------------------------------
+ * Replaces Softmax2d -> [:, :-1] -> PixelShuffle(r)   (XPoint.py:356-357).
+ * logits (B, r*r+1, Hc, Wc) in `dtype` -> prob (B, 1, r*Hc, r*Wc) fp32.  r <= 8.
+ */
+XP_API int xp_detector_post(const void* logits, float* prob, int64_t B, int64_t Hc, int64_t Wc, int32_t r,
+                     int32_t dtype, xp_stream_t stream);
+
+/* -- a7: descriptor head L2 normalisation ---------------------------------------------
+ * Replaces F.normalize(x, p=2, dim=1)   (XPoint.py:365-366).   x (B, C, HW) in `dtype` -> fp32.
+ * out_cf (B, C, HW) and/or out_cl (B, HW, C) (channel-last, the layout xp_sample_descriptors likes);
+ * either may be NULL.
+ */
+XP_API int xp_l2_normalize(const void* x, float* out_cf, float* out_cl, int64_t B, int64_t C, int64_t HW, int32_t dtype,
+                    xp_stream_t stream);
+
+/* -- a8/a9: greedy box NMS + top-k + keypoint compaction ------------------------------
+ * Replaces utils.box_nms (xpoint/utils/utils.py:148-192, i.e. torchvision.ops.nms/batched_nms on
+ * size x size boxes centred on every pixel above min_prob) and torch.nonzero(prob_nms > thr)
+ * (xpoint/utils/evaluation.py:281-282).  Bit-exact with sequential greedy NMS (ties: lower flat index
+ * wins).  prob (B, H, W) fp32 -> prob_nms (B, H, W) fp32 (zeros + kept scores; nullable).
+ * keypoints (B, kp_capacity, 2) int32 (y, x) in raster order and kp_count (B) int32 are optional
+ * (nullable); pixels counted are those with prob_nms > kp_threshold; kp_count holds the true count even
+ * if it exceeds kp_capacity (only the first kp_capacity are written).
+ * workspace: xp_nms_workspace_bytes(B, H, W) bytes of device memory.
+ */
+XP_API int64_t xp_nms_workspace_bytes(int64_t B, int64_t H, int64_t W);
+XP_API int xp_box_nms(const float* prob, float* prob_nms, int64_t B, int64_t H, int64_t W, float size, float min_prob,
+               float iou, int64_t keep_top_k, float kp_threshold, int32_t* keypoints, int32_t* kp_count,
+               int64_t kp_capacity, void* workspace, int64_t workspace_bytes, xp_stream_t stream);
+
+/* -- a10: bilinear descriptor sampling + L2 normalisation -----------------------------
+ * Replaces utils.interpolate_descriptors (xpoint/utils/utils.py:229-238: grid_sample bilinear,
+ * align_corners=True, zeros padding, then F.normalize).
+ * keypoints (B, kp_stride, 2) int32 (y, x); kp_count (B) int32 or NULL (then every image has kp_stride).
+ * desc: channel-first (B, C, Hc, Wc) or channel-last (B, Hc, Wc, C) fp32.   out (B, kp_stride, C) fp32;
+ * rows >= kp_count[b] are zero-filled.  H, W: full-resolution image size.
+ */
+XP_API int xp_sample_descriptors(const int32_t* keypoints, const int32_t* kp_count, int64_t B, int64_t kp_stride,
+                          const float* desc, int32_t channel_last, int64_t C, int64_t Hc, int64_t Wc, int64_t H,
+                          int64_t W, float* out, xp_stream_t stream);
+
+/* -- a11: mutual nearest-neighbour matching -------------------------------------------
+ * Replaces get_matches(d1, d2, 'bfmatcher', crossCheck=True) (xpoint/utils/matching.py:4-36,
+ * cv2.BFMatcher(NORM_L2, crossCheck=True).match) and NNMatcher.match (matching.py:38-75).
+ * d1 (P, n1_stride, C), d2 (P, n2_stride, C) fp32, C % 32 == 0, C <= 512; n1/n2 (P) int32 valid rows per pair
+ * (NULL = all).  Similarity GEMM on tcgen05 tensor cores (3xTF32 split, fp32-level accuracy), row / column
+ * arg-min of the squared L2 distance fused into the epilogue, ties -> lowest index.
+ * Outputs: nn12 (P, n1_stride) int32 = argmin_j, nn21 (P, n2_stride) int32 = argmin_i,
+ *          match_idx (P, n1_stride) int32 = nn12[i] if mutual else -1, match_dist (P, n1_stride) fp32 =
+ *          exact fp32 L2 distance of mutual pairs (recomputed on CUDA cores), match_count (P) int32.
+ * Any output pointer may be NULL.  workspace: xp_match_workspace_bytes(P, n1_stride, n2_stride, C).
+ * use_tensor_cores = 0 selects the exact-fp32 CUDA-core kernel (self-check path).
+ */
+XP_API int64_t xp_match_workspace_bytes(int64_t P, int64_t n1_stride, int64_t n2_stride, int64_t C);
+XP_API int xp_mnn_match(const float* d1, const float* d2, const int32_t* n1, const int32_t* n2, int64_t P,
+                 int64_t n1_stride, int64_t n2_stride, int64_t C, int32_t* nn12, int32_t* nn21, int32_t* match_idx,
+                 float* match_dist, int32_t* match_count, int32_t use_tensor_cores, void* workspace,
+                 int64_t workspace_bytes, xp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XPOINT_B200_H_ */

@@ -1,0 +1,186 @@
+"""Post-processing tail parity: detector post, NMS/top-k/keypoints (bit-exact), sampling, MNN matching (bit-exact)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close, golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _imports():
+    import xpoint_b200 as X
+    from oracle import oracle as O
+    return X, O
+
+
+def test_heads_golden():
+    X, _ = _imports()
+    g = golden("heads")
+    prob = X.detector_post(torch.from_numpy(g["logits"]).to(DEV))
+    np.testing.assert_allclose(prob.cpu().numpy(), g["prob"], rtol=1e-5, atol=1e-7)
+    d = X.normalize_descriptors(torch.from_numpy(g["desc_raw"]).to(DEV))
+    np.testing.assert_allclose(d.cpu().numpy(), g["desc"], rtol=1e-5, atol=1e-7)
+    d, dcl = X.normalize_descriptors(torch.from_numpy(g["desc_raw"]).to(DEV), channel_last_copy=True)
+    assert torch.equal(dcl, d.permute(0, 2, 3, 1).contiguous())
+    # 16-bit logits are widened first, like `.to(torch.float)` in XPoint.py:349
+    p16 = X.detector_post(torch.from_numpy(g["logits"]).to(DEV).half())
+    ref16 = torch.nn.PixelShuffle(8)(torch.softmax(torch.from_numpy(g["logits"]).half().float(), 1)[:, :-1])
+    np.testing.assert_allclose(p16.cpu().numpy(), ref16.numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_nms_golden_bit_exact():
+    X, _ = _imports()
+    g = golden("tail")
+    p = torch.from_numpy(g["prob"]).to(DEV)
+    pb = torch.from_numpy(g["prob_batched"]).to(DEV)
+    assert np.array_equal(X.box_nms(p, 8, 0.015).cpu().numpy(), g["nms8"])
+    assert np.array_equal(X.box_nms(p, 4, 0.015).cpu().numpy(), g["nms4"])
+    assert np.array_equal(X.box_nms(p, 8, 0.015, keep_top_k=50).cpu().numpy(), g["nms8_top50"])
+    assert np.array_equal(X.box_nms(p, 8, 0.015, iou=0.3).cpu().numpy(), g["nms8_iou03"])
+    assert np.array_equal(X.box_nms(pb, 8, 0.015, keep_top_k=40, on_cpu=True).cpu().numpy(), g["nms8_batched_top40"])
+    assert np.array_equal(X.box_nms(pb, 8, 0.015).cpu().numpy(), g["nms8_batched"])
+    res = X.nms_keypoints(p[None], 8, 0.015)
+    n = int(res.count[0])
+    assert np.array_equal(res.keypoints[0, :n].cpu().numpy().astype(np.int64), g["kp8"])   # raster order
+
+
+@pytest.mark.parametrize("H,W,B", [(256, 256, 2), (512, 640, 2), (1024, 1280, 1), (37, 53, 3)])
+@pytest.mark.parametrize("size,topk", [(8, 0), (8, 4096), (4, 0), (4, 16384), (8, 7)])
+def test_nms_vs_oracle_bit_exact(H, W, B, size, topk):
+    X, O = _imports()
+    g = torch.Generator().manual_seed(H + size + topk)
+    prob = torch.rand(B, 1, H, W, generator=g) ** 6          # SURVEY C.8/C.9 score maps, no exact ties
+    got = X.box_nms(prob.to(DEV), size, 0.015, keep_top_k=topk).cpu().numpy()
+    ref = O.box_nms(prob.numpy(), size, 0.015, keep_top_k=topk)
+    assert np.array_equal(got, ref)
+    res = X.nms_keypoints(prob[:, 0].to(DEV), size, 0.015, keep_top_k=topk, capacity=max(topk, 1) if topk else H * W)
+    for b in range(B):
+        kp = O.extract_keypoints(ref[b, 0], 0.015)
+        n = int(res.count[b])
+        assert n == len(kp)
+        assert np.array_equal(res.keypoints[b, :n].cpu().numpy().astype(np.int64), kp)
+
+
+def test_nms_ties_and_degenerate():
+    X, O = _imports()
+    # exact ties: lower flat index wins, plateau of equal scores
+    p = torch.zeros(1, 1, 24, 24)
+    p[0, 0, 5, 5] = p[0, 0, 5, 8] = 0.5
+    p[0, 0, 10:14, 10:14] = 0.25
+    p[0, 0, 20, 3] = 0.9
+    got = X.box_nms(p.to(DEV), 8, 0.015).cpu().numpy()
+    assert np.array_equal(got, O.box_nms(p.numpy(), 8, 0.015))
+    assert got[0, 0, 5, 5] == 0.5 and got[0, 0, 5, 8] == 0.0
+    # nothing above threshold / everything above threshold / monotone ramp (worst case for the fixed point)
+    z = torch.full((1, 1, 32, 40), 0.001)
+    assert X.box_nms(z.to(DEV), 8, 0.015).abs().sum() == 0
+    ramp = (torch.arange(48 * 64, dtype=torch.float32).reshape(1, 1, 48, 64) + 1) / (48 * 64)
+    assert np.array_equal(X.box_nms(ramp.to(DEV), 8, 0.015).cpu().numpy(), O.box_nms(ramp.numpy(), 8, 0.015))
+    assert np.array_equal(X.box_nms(ramp.to(DEV)[0, 0], 8, 0.015, keep_top_k=5).cpu().numpy(),
+                          O.box_nms(ramp.numpy()[0, 0], 8, 0.015, keep_top_k=5))
+    with pytest.raises(ValueError):
+        X.box_nms(torch.zeros(3, 4, 5, device=DEV), 8, 0.015)
+
+
+def test_interpolate_descriptors():
+    X, O = _imports()
+    g = golden("tail")
+    kp = torch.from_numpy(g["kp8"]).to(DEV)
+    d = X.interpolate_descriptors(kp, torch.from_numpy(g["desc_low"]).to(DEV), 96, 120)
+    np.testing.assert_allclose(d.cpu().numpy(), g["desc_kp"], rtol=0, atol=2e-6)
+    # batched, channel-last, ragged counts; zero rows past the count
+    gen = torch.Generator().manual_seed(0)
+    desc = torch.nn.functional.normalize(torch.randn(2, 256, 64, 80, generator=gen), dim=1)
+    kps = torch.stack([torch.randint(0, 512, (2, 300), generator=gen), torch.randint(0, 640, (2, 300), generator=gen)], -1)
+    cnt = torch.tensor([300, 123], dtype=torch.int32)
+    out = X.sample_descriptors(kps.to(DEV).int(), cnt.to(DEV), desc.to(DEV), 512, 640)
+    out_cl = X.sample_descriptors(kps.to(DEV).int(), cnt.to(DEV), desc.permute(0, 2, 3, 1).contiguous().to(DEV), 512, 640, True)
+    for b in range(2):
+        ref = O.interpolate_descriptors(kps[b, :cnt[b]].numpy(), desc[b].numpy(), 512, 640)
+        np.testing.assert_allclose(out[b, :cnt[b]].cpu().numpy(), ref, rtol=0, atol=2e-6)
+        np.testing.assert_allclose(out_cl[b, :cnt[b]].cpu().numpy(), ref, rtol=0, atol=2e-6)
+        assert out[b, cnt[b]:].abs().sum() == 0
+
+
+def _pairs(ms):
+    return [(m.queryIdx, m.trainIdx) for m in ms]
+
+
+@pytest.mark.parametrize("tc", [False, True])
+def test_match_golden_bit_exact(tc):
+    X, _ = _imports()
+    g = golden("match")
+    d1, d2 = torch.from_numpy(g["d1"]).to(DEV), torch.from_numpy(g["d2"]).to(DEV)
+    m = X.get_matches(d1, d2, "bfmatcher", crossCheck=True, use_tensor_cores=tc)
+    assert _pairs(m) == [tuple(p) for p in g["bf_pairs"].tolist()]
+    np.testing.assert_allclose([x.distance for x in m], g["bf_dist"], rtol=1e-5, atol=1e-6)
+    m2 = X.get_matches(g["d1"], g["d2"], "nnmatcher", threshold=10.0, use_tensor_cores=tc)   # numpy in, as the reference
+    assert _pairs(m2) == [tuple(p) for p in g["nn_pairs"].tolist()]
+    assert X.get_matches(d1[:0], d2, "bfmatcher", crossCheck=True) == []
+
+
+def _descs(n1, n2, seed):
+    g = torch.Generator().manual_seed(seed)
+    d1 = torch.nn.functional.normalize(torch.randn(n1, 256, generator=g), dim=1)
+    k = min(n1, n2) // 2
+    d2 = torch.randn(n2, 256, generator=g)
+    if k:
+        d2[:k] = d1[torch.randperm(n1, generator=g)[:k]] + 0.05 * torch.randn(k, 256, generator=g)
+    d2 = torch.nn.functional.normalize(d2, dim=1)[torch.randperm(n2, generator=g)]
+    return d1, d2
+
+
+@pytest.mark.parametrize("tc", [False, True])
+@pytest.mark.parametrize("n1,n2", [(1, 1), (1, 50), (971, 850), (4096, 4096), (300, 4000), (130, 257)])
+def test_match_vs_oracle_bit_exact(tc, n1, n2):
+    """Identical fp32 unit descriptors on both sides; pairs must be bit-exact wherever the float64 oracle's
+    best-vs-second gap is above fp32 noise (SURVEY C.13 min-gap guard, 1e-5 on squared distance)."""
+    X, O = _imports()
+    d1, d2 = _descs(n1, n2, n1 + n2)
+    q, t, dist, gap_r = O.mnn_match(d1.numpy(), d2.numpy(), return_gap=True)
+    _, _, _, gap_c = O.mnn_match(d2.numpy(), d1.numpy(), return_gap=True)
+    res = X.mnn_match(d1[None].to(DEV), d2[None].to(DEV), use_tensor_cores=tc)
+    idx = res.match_idx[0].cpu().numpy()
+    got = [(i, int(j)) for i, j in enumerate(idx) if j >= 0]
+    want = list(zip(q.tolist(), t.tolist()))
+    # rows / columns whose best and second-best neighbours are closer than fp32 summation noise are ambiguous
+    # for ANY fp32 implementation (OpenCV vs BLAS disagree there too); they are excluded, and must be rare
+    amb_r = set(np.nonzero(gap_r <= 1e-5)[0].tolist()) if n2 > 1 else set()
+    amb_c = set(np.nonzero(gap_c <= 1e-5)[0].tolist()) if n1 > 1 else set()
+    assert len(amb_r) <= 0.01 * n1 + 1 and len(amb_c) <= 0.01 * n2 + 1
+    keep = lambda pairs: [(i, j) for i, j in pairs if i not in amb_r and j not in amb_c]
+    assert keep(got) == keep(want)
+    if not amb_r and not amb_c:
+        assert got == want and int(res.count[0]) == len(want)
+    both = sorted(set(got) & set(want))
+    qi = np.array([i for i, _ in both], dtype=np.int64)
+    ref_d = {i: d for i, d in zip(q.tolist(), dist.tolist())}
+    np.testing.assert_allclose(res.match_dist[0].cpu().numpy()[qi], [ref_d[i] for i in qi.tolist()], rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("tc", [False, True])
+def test_match_batched_ragged_and_ties(tc):
+    X, O = _imports()
+    P, s1, s2 = 3, 200, 260
+    d1 = torch.zeros(P, s1, 256)
+    d2 = torch.zeros(P, s2, 256)
+    n1 = torch.tensor([200, 77, 0], dtype=torch.int32)
+    n2 = torch.tensor([260, 131, 40], dtype=torch.int32)
+    for p in range(P):
+        a, b = _descs(max(int(n1[p]), 1), int(n2[p]), 100 + p)
+        d1[p, :n1[p]] = a[:n1[p]]
+        d2[p, :n2[p]] = b
+    res = X.mnn_match(d1.to(DEV), d2.to(DEV), n1.to(DEV), n2.to(DEV), use_tensor_cores=tc)
+    for p in range(P):
+        q, t, _ = O.mnn_match(d1[p, :n1[p]].numpy(), d2[p, :n2[p]].numpy())
+        idx = res.match_idx[p].cpu().numpy()
+        assert [(i, int(j)) for i, j in enumerate(idx) if j >= 0] == list(zip(q.tolist(), t.tolist()))
+        assert int(res.count[p]) == len(q)
+    # duplicates resolve to the lowest index in both directions
+    base = torch.nn.functional.normalize(torch.randn(4, 256, generator=torch.Generator().manual_seed(0)), dim=1)
+    a = torch.stack([base[0], base[0], base[1]])
+    b = torch.stack([base[0], base[1], base[1]])
+    m = X.get_matches(a.to(DEV), b.to(DEV), "bfmatcher", crossCheck=True, use_tensor_cores=tc)
+    assert _pairs(m) == [(0, 0), (2, 1)]

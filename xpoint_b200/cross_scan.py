@@ -1,0 +1,133 @@
+"""CrossScan / CrossMerge operator API, call-compatible with xpoint/models/vmamba_src/csm_triton.py.
+
+``cross_scan_fn`` / ``cross_merge_fn`` (csm_triton.py:501-517) and the ``CrossScanF`` / ``CrossMergeF`` autograd
+Functions (csm_triton.py:182-273; the Triton twins ``CrossScanTritonF`` / ``CrossMergeTritonF`` :403-498 are aliases
+here) keep their names, argument order and output shapes.  The work is done by ``xp_cross_scan`` /
+``xp_cross_merge`` (include/xpoint_b200.h).  Forward only.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+def cross_scan_fwd(x: torch.Tensor, in_channel_first=True, out_channel_first=True, one_by_one=False, scans=0):
+    """x: (B,C,H,W) | (B,H,W,C) | (B,4,C,H,W) | (B,H,W,4,C)  ->  (B,4,C,L) | (B,L,4,C)."""
+    dev = _lib.require_cuda(x)
+    x = x.contiguous()
+    if one_by_one:
+        if in_channel_first:
+            B, K, C, H, W = x.shape
+        else:
+            B, H, W, K, C = x.shape
+        if K != 4:
+            raise RuntimeError("one_by_one cross scan expects 4 directions")
+    else:
+        if in_channel_first:
+            B, C, H, W = x.shape
+        else:
+            B, H, W, C = x.shape
+    shape = (B, 4, C, H * W) if out_channel_first else (B, H * W, 4, C)
+    xs = torch.empty(shape, dtype=x.dtype, device=dev)
+    if xs.numel():
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().xp_cross_scan(_lib.ptr(x), _lib.ptr(xs), B, C, H, W, _lib.dtype_code(x),
+                                                int(bool(in_channel_first)), int(bool(out_channel_first)),
+                                                int(bool(one_by_one)), int(scans), _lib.stream_ptr(dev)))
+        _lib.count_launches(1)
+    return xs
+
+
+def cross_merge_fwd(ys: torch.Tensor, in_channel_first=True, out_channel_first=True, one_by_one=False, scans=0):
+    """ys: (B,4,C,H,W) if out_channel_first else (B,H,W,4,C)  ->  (B,C,L) | (B,L,C)  [(B,4,C,L) | (B,L,4,C)].
+
+    Flag names follow the reference: ``out_channel_first`` describes ys, ``in_channel_first`` the result
+    (csm_triton.py:56-85)."""
+    dev = _lib.require_cuda(ys)
+    ys = ys.contiguous()
+    if out_channel_first:
+        B, K, C, H, W = ys.shape
+    else:
+        B, H, W, K, C = ys.shape
+    if K != 4:
+        raise RuntimeError("cross merge expects 4 directions")
+    L = H * W
+    if one_by_one:
+        shape = (B, 4, C, L) if in_channel_first else (B, L, 4, C)
+    else:
+        shape = (B, C, L) if in_channel_first else (B, L, C)
+    y = torch.empty(shape, dtype=ys.dtype, device=dev)
+    if y.numel():
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().xp_cross_merge(_lib.ptr(ys), _lib.ptr(y), B, C, H, W, _lib.dtype_code(ys),
+                                                 int(bool(out_channel_first)), int(bool(in_channel_first)),
+                                                 int(bool(one_by_one)), int(scans), _lib.stream_ptr(dev)))
+        _lib.count_launches(1)
+    return y
+
+
+class CrossScanF(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, in_channel_first=True, out_channel_first=True, one_by_one=False, scans=0):
+        return cross_scan_fwd(x, in_channel_first, out_channel_first, one_by_one, scans)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        raise NotImplementedError("xpoint_b200 is inference-only: CrossScan backward is not implemented")
+
+
+class CrossMergeF(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ys, in_channel_first=True, out_channel_first=True, one_by_one=False, scans=0):
+        return cross_merge_fwd(ys, in_channel_first, out_channel_first, one_by_one, scans)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        raise NotImplementedError("xpoint_b200 is inference-only: CrossMerge backward is not implemented")
+
+
+CrossScanTritonF = CrossScanF    # csm_triton.py:403 -- same contract, one CUDA implementation here
+CrossMergeTritonF = CrossMergeF  # csm_triton.py:456
+
+
+def cross_scan_fn(x, in_channel_first=True, out_channel_first=True, one_by_one=False, scans=0, force_torch=False):
+    """csm_triton.py:501-507.  ``force_torch`` is accepted for signature parity; there is one implementation."""
+    del force_torch
+    return CrossScanF.apply(x, in_channel_first, out_channel_first, one_by_one, scans)
+
+
+def cross_merge_fn(y, in_channel_first=True, out_channel_first=True, one_by_one=False, scans=0, force_torch=False):
+    """csm_triton.py:511-517."""
+    del force_torch
+    return CrossMergeF.apply(y, in_channel_first, out_channel_first, one_by_one, scans)
+
+
+def merge_norm_gate(ys: torch.Tensor, H: int, W: int, weight: torch.Tensor, bias: torch.Tensor, zact=None, eps=1e-5,
+                    out_dtype=None):
+    """Fused tail of the SS2D core: CrossMerge -> LayerNorm(d_inner) [-> * zact]  (VMamba.py:632-646, :364-372).
+
+    ys (B, 4, C, L) scan outputs;  zact (B, H, W, C) or None;  returns (B, H, W, C)."""
+    dev = _lib.require_cuda(ys, weight, bias, zact)
+    ys = ys.contiguous()
+    B, K, C, L = ys.shape
+    if K != 4 or L != H * W:
+        raise RuntimeError("merge_norm_gate expects ys of shape (B, 4, C, H*W)")
+    out_dtype = out_dtype or (zact.dtype if zact is not None else ys.dtype)
+    out = torch.empty((B, H, W, C), dtype=out_dtype, device=dev)
+    if zact is not None:
+        zact = zact.contiguous()
+        if zact.dtype != out_dtype or zact.numel() != out.numel():
+            raise RuntimeError("zact must match the output dtype and shape (B, H, W, C)")
+    if out.numel() == 0:
+        return out
+    lib = _lib.lib()
+    nbytes = lib.xp_merge_norm_gate_workspace_bytes(B, C, H, W)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.xp_merge_norm_gate(_lib.ptr(ys), _lib.ptr(weight.float().contiguous()),
+                                          _lib.ptr(bias.float().contiguous()), _lib.ptr(zact), _lib.ptr(out), B, C, H, W,
+                                          _lib.dtype_code(ys), _lib.dtype_code(out), float(eps), _lib.ptr(ws), nbytes,
+                                          _lib.stream_ptr(dev)))
+    _lib.count_launches(3)
+    return out

@@ -1,0 +1,220 @@
+// common.cuh -- shared device/host helpers for the sm_100a kernels of xpoint_b200.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/xpoint_b200.h"
+
+namespace xp {
+
+// ------------------------------------------------------------------------------------ errors
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* where);
+
+#define XP_REQUIRE(cond, ...)                \
+    do {                                     \
+        if (!(cond)) {                       \
+            ::xp::set_error(__VA_ARGS__);    \
+            return XP_ERR_INVALID_ARG;       \
+        }                                    \
+    } while (0)
+
+#define XP_CUDA_OK(expr)                                             \
+    do {                                                             \
+        cudaError_t _e = (expr);                                     \
+        if (_e != cudaSuccess) return ::xp::cuda_fail(_e, #expr);    \
+    } while (0)
+
+#define XP_LAUNCH_CHECK(name)                                        \
+    do {                                                             \
+        cudaError_t _e = cudaGetLastError();                         \
+        if (_e != cudaSuccess) return ::xp::cuda_fail(_e, name);     \
+    } while (0)
+
+int num_sms();
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int dtype_size(int dt) { return dt == XP_F32 ? 4 : 2; }
+
+// ------------------------------------------------------------------------------------ dtype conversion
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// Load V consecutive elements (V * sizeof(T) == 16 or 32 bytes for the vector paths) and widen to fp32.
+// p must be 16-byte aligned.
+template <typename T, int V> struct VecIO;
+
+template <> struct VecIO<float, 4> {
+    static __device__ __forceinline__ void load(const float* p, float (&r)[4]) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+        r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+    }
+    static __device__ __forceinline__ void load_stream(const float* p, float (&r)[4]) {
+        float4 v;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+        r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float (&r)[4]) {
+        asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+                     :: "l"(p), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]) : "memory");
+    }
+};
+
+template <> struct VecIO<__half, 8> {
+    static __device__ __forceinline__ void widen(const uint4& v, float (&r)[8]) {
+        const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); r[2 * i] = f.x; r[2 * i + 1] = f.y; }
+    }
+    static __device__ __forceinline__ void load(const __half* p, float (&r)[8]) {
+        widen(__ldg(reinterpret_cast<const uint4*>(p)), r);
+    }
+    static __device__ __forceinline__ void load_stream(const __half* p, float (&r)[8]) {
+        uint4 v;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+        widen(v, r);
+    }
+    static __device__ __forceinline__ void store(__half* p, const float (&r)[8]) {
+        uint4 v;
+        __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(r[2 * i], r[2 * i + 1]);
+        asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+                     :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    }
+};
+
+template <> struct VecIO<__nv_bfloat16, 8> {
+    static __device__ __forceinline__ void widen(const uint4& v, float (&r)[8]) {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {  // bf16 -> fp32 is a 16-bit shift
+            r[2 * i] = __uint_as_float(w[i] << 16);
+            r[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&r)[8]) {
+        widen(__ldg(reinterpret_cast<const uint4*>(p)), r);
+    }
+    static __device__ __forceinline__ void load_stream(const __nv_bfloat16* p, float (&r)[8]) {
+        uint4 v;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+        widen(v, r);
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&r)[8]) {
+        uint4 v;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(r[2 * i], r[2 * i + 1]);
+        asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+                     :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    }
+};
+
+// ------------------------------------------------------------------------------------ math
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// softplus(beta=1, threshold=20) as torch / the reference kernel define it
+// (csms6s.py:49-50, selective_scan_fwd_kernel_oflex.cuh:124-127).  log1pf keeps the small-delta regime
+// (dt in [1e-3, 0.1] after softplus, VMamba.py:181-186) accurate to fp32 rounding.
+__device__ __forceinline__ float softplus_f(float x) { return x > 20.0f ? x : log1pf(__expf(x)); }
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------ mbarrier / TMA (PTX)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    // try_wait sleeps in hardware; the bound turns a lost TMA completion into a trap instead of a hung GPU
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
+        if (spins > (1u << 26)) __trap();
+}
+
+// 4-D tiled TMA load: global (tensor map, coords c0 innermost) -> shared, completion on mbarrier.
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+           "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+// 4-D tiled TMA store: shared -> global.
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 :: "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory");
+}
+template <int N> __device__ __forceinline__ void tma_store_wait() {
+    asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// ------------------------------------------------------------------------------------ host: tensor maps
+// cuTensorMapEncodeTiled resolved through the runtime (no link-time dependency on libcuda).
+// dims/strides innermost-first; strides_bytes has rank-1 entries (dim 1..rank-1).  Returns XP_OK or error.
+int make_tensor_map(CUtensorMap* map, int dtype, int rank, const void* base, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, int swizzle_128b);
+
+}  // namespace xp

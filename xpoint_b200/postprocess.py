@@ -1,0 +1,230 @@
+"""Post-processing tail, call-compatible with the reference's utility functions.
+
+  box_nms(prob, size, min_prob, iou=0.1, keep_top_k=0, on_cpu=False)      xpoint/utils/utils.py:148-192
+  interpolate_descriptors(keypoints, descriptors_lowres, H, W)            xpoint/utils/utils.py:229-238
+  get_matches(desc_1, desc_2, method='bfmatcher', knn_matches=False, **kw) xpoint/utils/matching.py:4-36
+  NNMatcher(threshold).match(desc1, desc2)                                 xpoint/utils/matching.py:38-75
+  detector_post(logits) / normalize_descriptors(x)                         XPoint.py:356-357 / :365-366
+
+plus batched, sync-free variants used by the pair pipeline (``nms_keypoints``, ``sample_descriptors``,
+``mnn_match``).  Everything runs on the GPU through libxpoint_b200.so; there is no CPU path (``on_cpu`` is accepted
+and ignored, the result stays on the input's device exactly as the reference returns it there).
+"""
+from __future__ import annotations
+
+from typing import NamedTuple, Optional
+
+import torch
+
+from . import _lib
+
+
+# ------------------------------------------------------------------------------------------ heads
+def detector_post(logits: torch.Tensor, r: int = 8) -> torch.Tensor:
+    """Softmax2d -> drop dustbin -> PixelShuffle(r).  (B, r*r+1, Hc, Wc) -> (B, 1, r*Hc, r*Wc) fp32."""
+    dev = _lib.require_cuda(logits)
+    logits = logits.contiguous()
+    B, Cn, Hc, Wc = logits.shape
+    if Cn != r * r + 1:
+        raise RuntimeError(f"detector_post: expected {r * r + 1} channels, got {Cn}")
+    prob = torch.empty((B, 1, Hc * r, Wc * r), dtype=torch.float32, device=dev)
+    if prob.numel():
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().xp_detector_post(_lib.ptr(logits), _lib.ptr(prob), B, Hc, Wc, r, _lib.dtype_code(logits),
+                                                   _lib.stream_ptr(dev)))
+        _lib.count_launches(1)
+    return prob
+
+
+def normalize_descriptors(x: torch.Tensor, channel_last_copy: bool = False):
+    """F.normalize(x, p=2, dim=1) for (B, C, H, W); optionally also returns a (B, H, W, C) copy."""
+    dev = _lib.require_cuda(x)
+    x = x.contiguous()
+    B, C, H, W = x.shape
+    out = torch.empty((B, C, H, W), dtype=torch.float32, device=dev)
+    out_cl = torch.empty((B, H, W, C), dtype=torch.float32, device=dev) if channel_last_copy else None
+    if out.numel():
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().xp_l2_normalize(_lib.ptr(x), _lib.ptr(out), _lib.ptr(out_cl), B, C, H * W,
+                                                  _lib.dtype_code(x), _lib.stream_ptr(dev)))
+        _lib.count_launches(1)
+    return (out, out_cl) if channel_last_copy else out
+
+
+# ------------------------------------------------------------------------------------------ NMS
+class Keypoints(NamedTuple):
+    prob_nms: Optional[torch.Tensor]   # (B, H, W) fp32 or None
+    keypoints: torch.Tensor            # (B, capacity, 2) int32 (y, x), raster order, rows >= count undefined
+    count: torch.Tensor                # (B,) int32
+
+
+def nms_keypoints(prob: torch.Tensor, size, min_prob, iou=0.1, keep_top_k=0, kp_threshold=None, capacity=None,
+                  want_map=True) -> Keypoints:
+    """Batched NMS + top-k + raster-order keypoint compaction in one launch, no host sync.  prob (B,H,W)."""
+    dev = _lib.require_cuda(prob)
+    if prob.dtype != torch.float32:
+        prob = prob.float()
+    prob = prob.contiguous()
+    B, H, W = prob.shape
+    kp_threshold = float(min_prob if kp_threshold is None else kp_threshold)
+    if capacity is None:
+        capacity = keep_top_k if keep_top_k > 0 else H * W
+    out = torch.empty_like(prob) if want_map else None
+    kp = torch.empty((B, capacity, 2), dtype=torch.int32, device=dev)
+    cnt = torch.zeros((B,), dtype=torch.int32, device=dev)
+    if B:
+        lib = _lib.lib()
+        nbytes = lib.xp_nms_workspace_bytes(B, H, W)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.xp_box_nms(_lib.ptr(prob), _lib.ptr(out), B, H, W, float(size), float(min_prob), float(iou),
+                                      int(keep_top_k), kp_threshold, _lib.ptr(kp), _lib.ptr(cnt), capacity, _lib.ptr(ws),
+                                      nbytes, _lib.stream_ptr(dev)))
+        _lib.count_launches(1)
+    return Keypoints(out, kp, cnt)
+
+
+def box_nms(prob, size, min_prob, iou=0.1, keep_top_k=0, on_cpu=False):
+    """Drop-in for utils.box_nms: prob (H,W) or (B,1,H,W) -> same shape, zeros + surviving scores."""
+    del on_cpu
+    if prob.dim() not in (2, 4):
+        raise ValueError("The probability must be either 2D (H,W), or 4D (B, 1, H, W)")
+    shape = prob.shape
+    if prob.dim() == 4 and shape[1] != 1:
+        raise ValueError("The probability must be either 2D (H,W), or 4D (B, 1, H, W)")
+    res = nms_keypoints(prob.reshape(-1, shape[-2], shape[-1]), size, min_prob, iou, keep_top_k, capacity=1)
+    return res.prob_nms.reshape(shape).to(prob.dtype)
+
+
+# ------------------------------------------------------------------------------------------ sampling
+def sample_descriptors(keypoints: torch.Tensor, count: Optional[torch.Tensor], desc: torch.Tensor, H: int, W: int,
+                       channel_last: bool = False) -> torch.Tensor:
+    """Batched bilinear sampling + L2 norm.  keypoints (B, n, 2) int32 (y, x); desc (B,C,Hc,Wc) or (B,Hc,Wc,C)."""
+    dev = _lib.require_cuda(keypoints, count, desc)
+    keypoints = keypoints.to(torch.int32).contiguous()
+    desc = desc.float().contiguous()
+    B, n = keypoints.shape[:2]
+    if channel_last:
+        _, Hc, Wc, C = desc.shape
+    else:
+        _, C, Hc, Wc = desc.shape
+    if desc.shape[0] != B:
+        raise RuntimeError("sample_descriptors: batch mismatch between keypoints and descriptors")
+    out = torch.empty((B, n, C), dtype=torch.float32, device=dev)
+    if out.numel():
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().xp_sample_descriptors(_lib.ptr(keypoints), _lib.ptr(count), B, n, _lib.ptr(desc),
+                                                        int(channel_last), C, Hc, Wc, H, W, _lib.ptr(out),
+                                                        _lib.stream_ptr(dev)))
+        _lib.count_launches(1)
+    return out
+
+
+def interpolate_descriptors(keypoints, descriptors_lowres, H, W):
+    """Drop-in for utils.interpolate_descriptors: keypoints (N,2) (y,x); descriptors (C,Hc,Wc) -> (N,C)."""
+    kp = keypoints.to(torch.int32).reshape(1, -1, 2)
+    return sample_descriptors(kp, None, descriptors_lowres.unsqueeze(0), int(H), int(W))[0]
+
+
+# ------------------------------------------------------------------------------------------ matching
+class Matches(NamedTuple):
+    match_idx: torch.Tensor    # (P, n1) int32: train index of the mutual match of query i, or -1
+    match_dist: torch.Tensor   # (P, n1) fp32 L2 distance (0 where unmatched)
+    count: torch.Tensor        # (P,) int32
+    nn12: torch.Tensor         # (P, n1) int32
+    nn21: torch.Tensor         # (P, n2) int32
+
+
+def mnn_match(d1: torch.Tensor, d2: torch.Tensor, n1: Optional[torch.Tensor] = None, n2: Optional[torch.Tensor] = None,
+              use_tensor_cores: bool = True) -> Matches:
+    """Batched mutual-NN matching.  d1 (P, n1, C), d2 (P, n2, C) fp32; n1/n2 (P,) int32 valid counts or None."""
+    dev = _lib.require_cuda(d1, d2, n1, n2)
+    d1 = d1.float().contiguous()
+    d2 = d2.float().contiguous()
+    P, s1, C = d1.shape
+    s2 = d2.shape[1]
+    if d2.shape[0] != P or d2.shape[2] != C:
+        raise RuntimeError("mnn_match: d1 and d2 must be (P, n, C) with equal P and C")
+    nn12 = torch.full((P, s1), -1, dtype=torch.int32, device=dev)
+    nn21 = torch.full((P, s2), -1, dtype=torch.int32, device=dev)
+    midx = torch.full((P, s1), -1, dtype=torch.int32, device=dev)
+    mdist = torch.zeros((P, s1), dtype=torch.float32, device=dev)
+    cnt = torch.zeros((P,), dtype=torch.int32, device=dev)
+    if P and s1 and s2:
+        lib = _lib.lib()
+        nbytes = lib.xp_match_workspace_bytes(P, s1, s2, C)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        n1 = None if n1 is None else n1.to(torch.int32).contiguous()
+        n2 = None if n2 is None else n2.to(torch.int32).contiguous()
+        with torch.cuda.device(dev):
+            _lib.check(lib.xp_mnn_match(_lib.ptr(d1), _lib.ptr(d2), _lib.ptr(n1), _lib.ptr(n2), P, s1, s2, C,
+                                        _lib.ptr(nn12), _lib.ptr(nn21), _lib.ptr(midx), _lib.ptr(mdist), _lib.ptr(cnt),
+                                        int(bool(use_tensor_cores)), _lib.ptr(ws), nbytes, _lib.stream_ptr(dev)))
+        _lib.count_launches(5)   # 2 row-norm + 2 arg-min (or 1 fused + 1 decode) + mutual check
+    return Matches(midx, mdist, cnt, nn12, nn21)
+
+
+class DMatch(NamedTuple):
+    """Field-compatible with cv2.DMatch as the reference consumes it (queryIdx, trainIdx, distance)."""
+    queryIdx: int
+    trainIdx: int
+    distance: float
+    imgIdx: int = 0
+
+
+def _to_matches(res: Matches, max_dist: Optional[float] = None):
+    idx = res.match_idx[0]
+    q = torch.nonzero(idx >= 0).flatten()
+    t = idx[q]
+    d = res.match_dist[0][q]
+    if max_dist is not None:
+        keep = d < max_dist
+        q, t, d = q[keep], t[keep], d[keep]
+    return [DMatch(int(a), int(b), float(c)) for a, b, c in zip(q.tolist(), t.tolist(), d.tolist())]
+
+
+def _as_cuda_desc(d):
+    if not torch.is_tensor(d):
+        d = torch.as_tensor(d)          # numpy in the reference's call sites (evaluation.py:287-291)
+    if not d.is_cuda:
+        if not torch.cuda.is_available():
+            raise RuntimeError("xpoint_b200: no CUDA device; descriptor matching has no CPU path")
+        d = d.cuda(non_blocking=True)
+    return d.float()
+
+
+class NNMatcher:
+    """matching.py:38-75: mutual NN + distance threshold (0.7 default)."""
+
+    def __init__(self, threshold=0.7, use_tensor_cores=True):
+        if threshold < 0.0:
+            raise ValueError("'threshold' should be non-negative")
+        self.nn_thresh = threshold
+        self.use_tensor_cores = use_tensor_cores
+
+    def match(self, desc1, desc2):
+        if desc1.shape[0] == 0 or desc2.shape[0] == 0:
+            return []
+        res = mnn_match(_as_cuda_desc(desc1)[None], _as_cuda_desc(desc2)[None], use_tensor_cores=self.use_tensor_cores)
+        return _to_matches(res, self.nn_thresh)
+
+
+def get_matches(desc_1, desc_2, method="bfmatcher", knn_matches=False, **kwargs):
+    """Drop-in for matching.get_matches for the mutual-NN methods the XPoint evaluation uses:
+    ``method='bfmatcher'`` with ``crossCheck=True`` and ``method='nnmatcher'``.  Returns DMatch-like tuples in
+    increasing queryIdx.  Other methods (flann, knn ratio test, thresholdmatcher) are outside the hot path."""
+    if knn_matches:
+        raise NotImplementedError("knn_matches / ratio test is outside the accelerated hot path")
+    if desc_1.shape[0] == 0 or desc_2.shape[0] == 0:
+        return []
+    use_tc = kwargs.pop("use_tensor_cores", True)
+    if method == "bfmatcher":
+        if not kwargs.pop("crossCheck", False):
+            raise NotImplementedError("bfmatcher without crossCheck is outside the accelerated hot path")
+        res = mnn_match(_as_cuda_desc(desc_1)[None], _as_cuda_desc(desc_2)[None], use_tensor_cores=use_tc)
+        return _to_matches(res)
+    if method == "nnmatcher":
+        return NNMatcher(use_tensor_cores=use_tc, **kwargs).match(desc_1, desc_2)
+    if method in ("flann", "thresholdmatcher"):
+        raise NotImplementedError(f"method {method!r} is outside the accelerated hot path")
+    raise ValueError("unknown matching method")

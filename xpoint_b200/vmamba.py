@@ -1,0 +1,326 @@
+"""VMamba encoder blocks around the B200 SS2D hot path.
+
+Host-side mirror of the parts of xpoint/models/vmamba_src/VMamba.py that XPoint instantiates:
+``SS2D`` (VMamba.py:1107-1149; forward types ``v0`` :305-374 and the ``v2`` family ``v01..v05/v2/v3`` with the
+``_noz/_nozact/_oact/_no32`` postfixes :380-664), ``VSSBlock`` (:1153-1240) and ``VSSM`` (:1243-1525), with
+identical constructor keywords and state_dict keys/shapes so reference checkpoints load.
+
+What is ours: the SS2D core -- CrossScan -> selective scan -> CrossMerge -> out_norm [-> gate] -- runs on the
+hand-written sm_100a kernels of libxpoint_b200.so.  What stays a library call ("OUT OF SCOPE ...
+library call; stays a library call"): the dense projections / convolutions / LayerNorms around it
+(torch -> cuBLAS / cuDNN).  There is no CPU path: calling a module on CPU tensors raises.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from functools import partial
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .cross_scan import cross_scan_fn, merge_norm_gate
+from .selective_scan import selective_scan_fn
+
+
+class Permute(nn.Module):
+    def __init__(self, *args):
+        super().__init__()
+        self.args = args
+
+    def forward(self, x):
+        return x.permute(*self.args)
+
+
+class Mlp(nn.Module):  # VMamba.py:110-128 (channel-last only; XPoint never builds channel-first VSSMs)
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.0, channels_first=False):
+        super().__init__()
+        assert not channels_first
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.act = act_layer()
+        self.fc2 = nn.Linear(hidden_features, out_features)
+
+    def forward(self, x):
+        return self.fc2(self.act(self.fc1(x)))
+
+
+class PatchMerging2D(nn.Module):  # VMamba.py:60-98, channel-last
+    def __init__(self, dim, out_dim=-1, norm_layer=nn.LayerNorm, channel_first=False):
+        super().__init__()
+        assert not channel_first
+        self.reduction = nn.Linear(4 * dim, (2 * dim) if out_dim < 0 else out_dim, bias=False)
+        self.norm = norm_layer(4 * dim)
+
+    def forward(self, x):
+        H, W, _ = x.shape[-3:]
+        if (W % 2 != 0) or (H % 2 != 0):
+            x = F.pad(x, (0, 0, 0, W % 2, 0, H % 2))
+        x = torch.cat([x[..., 0::2, 0::2, :], x[..., 1::2, 0::2, :], x[..., 0::2, 1::2, :], x[..., 1::2, 1::2, :]], -1)
+        return self.reduction(self.norm(x))
+
+
+def _init_dt_A_D(d_state, dt_rank, d_inner, dt_scale=1.0, dt_init="random", dt_min=0.001, dt_max=0.1,
+                 dt_init_floor=1e-4, k_group=4):
+    """Same distributions as mamba_init.init_dt_A_D (VMamba.py:165-232)."""
+    ws, bs = [], []
+    std = dt_rank ** -0.5 * dt_scale
+    for _ in range(k_group):
+        w = torch.empty(d_inner, dt_rank)
+        if dt_init == "constant":
+            nn.init.constant_(w, std)
+        else:
+            nn.init.uniform_(w, -std, std)
+        dt = torch.exp(torch.rand(d_inner) * (math.log(dt_max) - math.log(dt_min)) + math.log(dt_min)).clamp(min=dt_init_floor)
+        ws.append(w)
+        bs.append(dt + torch.log(-torch.expm1(-dt)))  # softplus^-1
+    A_logs = torch.log(torch.arange(1, d_state + 1, dtype=torch.float32)).view(1, -1).repeat(k_group * d_inner, 1)
+    Ds = torch.ones(k_group * d_inner)
+    return nn.Parameter(A_logs), nn.Parameter(Ds), nn.Parameter(torch.stack(ws)), nn.Parameter(torch.stack(bs))
+
+
+class SS2D(nn.Module):
+    """Constructor keywords and parameter names of VMamba.SS2D (VMamba.py:1107-1149)."""
+
+    def __init__(self, d_model=96, d_state=16, ssm_ratio=2.0, dt_rank="auto", act_layer=nn.SiLU, d_conv=3, conv_bias=True,
+                 dropout=0.0, bias=False, dt_min=0.001, dt_max=0.1, dt_init="random", dt_scale=1.0, dt_init_floor=1e-4,
+                 initialize="v0", forward_type="v2", channel_first=False, **kwargs):
+        super().__init__()
+        if channel_first:
+            raise NotImplementedError("channel_first SS2D is not used by XPoint and is not built")
+        if dropout > 0.0:
+            raise NotImplementedError("inference-only: dropout must be 0")
+        self.k_group = 4
+        self.d_model, self.d_state = int(d_model), int(d_state)
+        self.d_inner = int(ssm_ratio * d_model)
+        self.dt_rank = int(math.ceil(d_model / 16) if dt_rank == "auto" else dt_rank)
+        ft = forward_type
+        if ft in ("v0", "v0seq"):
+            # SS2Dv0 (VMamba.py:236-303): z gate with SiLU, conv bias on, fp32 scan inputs, mamba-style output dtype
+            self.family = "v0"
+            self.disable_z = self.disable_z_act = self.oact = False
+            self.force_fp32, self.oflex = True, False
+            d_conv, conv_bias, bias, act_layer = 3, True, False, nn.SiLU
+            initialize = "v0"
+        else:
+            self.family = "v2"
+
+            def cut(tag, value):
+                hit = value.endswith(tag)
+                return hit, (value[: -len(tag)] if hit else value)
+
+            disable_force32, ft = cut("_no32", ft)
+            self.oact, ft = cut("_oact", ft)
+            self.disable_z, ft = cut("_noz", ft)
+            self.disable_z_act, ft = cut("_nozact", ft)
+            for tag in ("_onnone", "_ondwconv3", "_oncnorm", "_onsoftmax", "_onsigmoid"):
+                if ft.endswith(tag):
+                    raise NotImplementedError(f"out_norm variant {tag} is not used by XPoint and is not built")
+            table = dict(v01=(not disable_force32, False), v02=(not disable_force32, False), v03=(not disable_force32, True),
+                         v04=(False, True), v05=(False, True), v2=(not disable_force32, False), v3=(False, True))
+            if ft not in table:
+                raise NotImplementedError(f"SS2D forward_type {forward_type!r} is outside the hot path (supported: v0, "
+                                          f"{', '.join(table)} with _noz/_nozact/_oact/_no32)")
+            self.force_fp32, self.oflex = table[ft]
+        self.forward_type = forward_type
+        self.with_dconv = d_conv > 1
+        d_proj = self.d_inner if self.disable_z else 2 * self.d_inner
+        self.in_proj = nn.Linear(self.d_model, d_proj, bias=bias)
+        self.act = act_layer()
+        if self.with_dconv:
+            self.conv2d = nn.Conv2d(self.d_inner, self.d_inner, groups=self.d_inner, bias=conv_bias, kernel_size=d_conv,
+                                    padding=(d_conv - 1) // 2)
+        self.x_proj_weight = nn.Parameter(torch.stack([
+            nn.Linear(self.d_inner, self.dt_rank + 2 * self.d_state, bias=False).weight.detach() for _ in range(self.k_group)]))
+        self.out_act = nn.GELU() if self.oact else nn.Identity()
+        self.out_norm = nn.LayerNorm(self.d_inner)
+        self.out_proj = nn.Linear(self.d_inner, self.d_model, bias=bias)
+        if initialize == "v0":
+            self.A_logs, self.Ds, self.dt_projs_weight, self.dt_projs_bias = _init_dt_A_D(
+                self.d_state, self.dt_rank, self.d_inner, dt_scale, dt_init, dt_min, dt_max, dt_init_floor, self.k_group)
+        elif initialize == "v1":
+            self.Ds = nn.Parameter(torch.ones(self.k_group * self.d_inner))
+            self.A_logs = nn.Parameter(torch.randn(self.k_group * self.d_inner, self.d_state))
+            self.dt_projs_weight = nn.Parameter(0.1 * torch.randn(self.k_group, self.d_inner, self.dt_rank))
+            self.dt_projs_bias = nn.Parameter(0.1 * torch.randn(self.k_group, self.d_inner))
+        else:
+            self.Ds = nn.Parameter(torch.ones(self.k_group * self.d_inner))
+            self.A_logs = nn.Parameter(torch.zeros(self.k_group * self.d_inner, self.d_state))
+            self.dt_projs_weight = nn.Parameter(0.1 * torch.rand(self.k_group, self.d_inner, self.dt_rank))
+            self.dt_projs_bias = nn.Parameter(0.1 * torch.rand(self.k_group, self.d_inner))
+
+    # -------------------------------------------------------------------------------------------------------
+    def forward_core(self, x: torch.Tensor, zact=None) -> torch.Tensor:
+        """x (B, d_inner, H, W) -> (B, H, W, d_inner): the hot path of VMamba.py:493-646 / :314-372.
+
+        CrossScan, selective scan and CrossMerge + out_norm (+ gate) are libxpoint_b200 kernels; the two small
+        projections x_proj / dt_proj stay grouped 1x1 convolutions (cuDNN/cuBLAS), as in the reference's
+        ``no_einsum`` path (VMamba.py:605-608)."""
+        B, D, H, W = x.shape
+        K, N, R, L = self.k_group, self.d_state, self.dt_rank, H * W
+        xs = cross_scan_fn(x, True, True, False, 0)                                        # (B, 4, D, L)
+        x_dbl = F.conv1d(xs.view(B, -1, L), self.x_proj_weight.view(-1, D, 1), bias=None, groups=K)
+        dts, Bs, Cs = torch.split(x_dbl.view(B, K, -1, L), [R, N, N], dim=2)
+        dts = F.conv1d(dts.contiguous().view(B, -1, L), self.dt_projs_weight.view(K * D, -1, 1), groups=K)
+        us = xs.view(B, -1, L)
+        if dts.dtype != us.dtype:
+            dts = dts.to(us.dtype)
+        if Bs.dtype != us.dtype:
+            Bs, Cs = Bs.to(us.dtype), Cs.to(us.dtype)
+        if self.force_fp32:
+            us, dts, Bs, Cs = us.float(), dts.float(), Bs.float(), Cs.float()
+        As = -self.A_logs.float().exp()
+        ys = selective_scan_fn(us, dts, As, Bs, Cs, self.Ds.float(), self.dt_projs_bias.float().view(-1), True,
+                               True if self.family == "v0" else self.oflex, None)       # (B, 4*D, L)
+        return merge_norm_gate(ys.view(B, K, D, L), H, W, self.out_norm.weight, self.out_norm.bias, zact,
+                               self.out_norm.eps, out_dtype=x.dtype)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x (B, H, W, d_model) -> (B, H, W, d_model)   (forwardv0 VMamba.py:305-374, forwardv2 :648-664)."""
+        x = self.in_proj(x)
+        z = None
+        if not self.disable_z:
+            x, z = x.chunk(2, dim=-1)
+            if not self.disable_z_act:
+                z = self.act(z)
+        x = x.permute(0, 3, 1, 2).contiguous()
+        if self.with_dconv:
+            x = self.conv2d(x)
+        x = self.act(x)
+        if isinstance(self.out_act, nn.Identity) and z is not None:
+            y = self.forward_core(x, zact=z.contiguous().to(x.dtype))
+        else:
+            y = self.out_act(self.forward_core(x))
+            if z is not None:
+                y = y * z
+        return self.out_proj(y)
+
+
+class VSSBlock(nn.Module):  # VMamba.py:1153-1240
+    def __init__(self, hidden_dim=0, drop_path=0.0, norm_layer=nn.LayerNorm, channel_first=False, ssm_d_state=16,
+                 ssm_ratio=2.0, ssm_dt_rank="auto", ssm_act_layer=nn.SiLU, ssm_conv=3, ssm_conv_bias=True, ssm_drop_rate=0.0,
+                 ssm_init="v0", forward_type="v2", mlp_ratio=4.0, mlp_act_layer=nn.GELU, mlp_drop_rate=0.0, gmlp=False,
+                 use_checkpoint=False, post_norm=False, **kwargs):
+        super().__init__()
+        if gmlp or post_norm:
+            raise NotImplementedError("gmlp / post_norm are not used by XPoint and are not built")
+        self.ssm_branch = ssm_ratio > 0
+        self.mlp_branch = mlp_ratio > 0
+        if self.ssm_branch:
+            self.norm = norm_layer(hidden_dim)
+            self.op = SS2D(d_model=hidden_dim, d_state=ssm_d_state, ssm_ratio=ssm_ratio, dt_rank=ssm_dt_rank,
+                           act_layer=ssm_act_layer, d_conv=ssm_conv, conv_bias=ssm_conv_bias, dropout=ssm_drop_rate,
+                           initialize=ssm_init, forward_type=forward_type, channel_first=channel_first)
+        if self.mlp_branch:
+            self.norm2 = norm_layer(hidden_dim)
+            self.mlp = Mlp(hidden_dim, int(hidden_dim * mlp_ratio), act_layer=mlp_act_layer, drop=mlp_drop_rate)
+
+    def forward(self, x):  # drop_path is the identity in eval mode (inference tier)
+        if self.ssm_branch:
+            x = x + self.op(self.norm(x))
+        if self.mlp_branch:
+            x = x + self.mlp(self.norm2(x))
+        return x
+
+
+class VSSM(nn.Module):
+    """VMamba.VSSM as XPoint uses it (VMamba.py:1243-1525): no classifier, output (B, dims[-1]/16, H/8, W/8)."""
+
+    def __init__(self, patch_size=4, in_chans=3, num_classes=1000, depths=(2, 2, 9, 2), dims=(96, 192, 384, 768),
+                 ssm_d_state=16, ssm_ratio=2.0, ssm_dt_rank="auto", ssm_act_layer="silu", ssm_conv=3, ssm_conv_bias=True,
+                 ssm_drop_rate=0.0, ssm_init="v0", forward_type="v2", mlp_ratio=4.0, mlp_act_layer="gelu", mlp_drop_rate=0.0,
+                 gmlp=False, drop_path_rate=0.1, patch_norm=True, norm_layer="LN", downsample_version="v2",
+                 patchembed_version="v1", use_checkpoint=False, posembed=False, imgsize=224, **kwargs):
+        super().__init__()
+        if norm_layer.lower() != "ln":
+            raise NotImplementedError("only channel-last LayerNorm VSSMs are built (XPoint uses norm_layer='ln')")
+        if posembed:
+            raise NotImplementedError("posembed is not used by XPoint and is not built")
+        self.in_chans = in_chans
+        depths = list(depths)
+        self.num_layers = len(depths)
+        if isinstance(dims, int):
+            dims = [int(dims * 2 ** i) for i in range(self.num_layers)]
+        self.dims = list(dims)
+        acts = dict(silu=nn.SiLU, gelu=nn.GELU, relu=nn.ReLU, sigmoid=nn.Sigmoid)
+        ssm_act, mlp_act = acts[ssm_act_layer.lower()], acts[mlp_act_layer.lower()]
+        LN = nn.LayerNorm
+        if patchembed_version == "v1":
+            self.patch_embed = nn.Sequential(
+                nn.Conv2d(in_chans, dims[0], kernel_size=patch_size, stride=patch_size, bias=True), Permute(0, 2, 3, 1),
+                (LN(dims[0]) if patch_norm else nn.Identity()))
+        else:
+            s = patch_size // 2
+            k = s + 1
+            self.patch_embed = nn.Sequential(
+                nn.Conv2d(in_chans, dims[0] // 2, kernel_size=k, stride=s, padding=1),
+                (Permute(0, 2, 3, 1) if patch_norm else nn.Identity()),
+                (LN(dims[0] // 2) if patch_norm else nn.Identity()),
+                (Permute(0, 3, 1, 2) if patch_norm else nn.Identity()),
+                nn.GELU(),
+                nn.Conv2d(dims[0] // 2, dims[0], kernel_size=k, stride=s, padding=1), Permute(0, 2, 3, 1),
+                (LN(dims[0]) if patch_norm else nn.Identity()))
+
+        def downsample(dim, out_dim):
+            if downsample_version == "v1":
+                return PatchMerging2D(dim, out_dim, LN)
+            if downsample_version == "v2":
+                return nn.Sequential(Permute(0, 3, 1, 2), nn.Conv2d(dim, out_dim, kernel_size=2, stride=2),
+                                     Permute(0, 2, 3, 1), LN(out_dim))
+            if downsample_version == "v3":
+                return nn.Sequential(Permute(0, 3, 1, 2), nn.Conv2d(dim, out_dim, kernel_size=3, stride=2, padding=1),
+                                     Permute(0, 2, 3, 1), LN(out_dim))
+            raise NotImplementedError(downsample_version)
+
+        self.layers = nn.ModuleList()
+        for i in range(self.num_layers):
+            blocks = [VSSBlock(hidden_dim=self.dims[i], norm_layer=LN, ssm_d_state=ssm_d_state, ssm_ratio=ssm_ratio,
+                               ssm_dt_rank=ssm_dt_rank, ssm_act_layer=ssm_act, ssm_conv=ssm_conv, ssm_conv_bias=ssm_conv_bias,
+                               ssm_drop_rate=ssm_drop_rate, ssm_init=ssm_init, forward_type=forward_type, mlp_ratio=mlp_ratio,
+                               mlp_act_layer=mlp_act, mlp_drop_rate=mlp_drop_rate, gmlp=gmlp) for _ in range(depths[i])]
+            ds = downsample(self.dims[i], self.dims[i + 1]) if i < self.num_layers - 1 else nn.Identity()
+            self.layers.append(nn.Sequential(OrderedDict(blocks=nn.Sequential(*blocks), downsample=ds)))
+        self.apply(self._init_weights)
+
+    @staticmethod
+    def _init_weights(m):
+        if isinstance(m, nn.Linear):
+            nn.init.trunc_normal_(m.weight, std=0.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    @staticmethod
+    def depth_to_space(x, bs):  # VMamba.py:1500-1505
+        N, C, H, W = x.size()
+        x = x.view(N, bs, bs, C // (bs * bs), H, W).permute(0, 3, 4, 1, 5, 2).contiguous()
+        return x.view(N, C // (bs * bs), H * bs, W * bs)
+
+    def forward(self, x):
+        if self.in_chans == 3 and x.shape[1] == 1:
+            x = torch.cat((x, x, x), dim=1)
+        x = self.patch_embed(x)
+        for layer in self.layers:
+            x = layer(x)
+        return self.depth_to_space(x.permute(0, 3, 1, 2), 4)
+
+
+# presets: SURVEY section 8, "V" = vanilla_vmamba_tiny (VMamba.py:1651-1662), "E" = shipped XPoint-EXP1
+# (model_weights/XPoint-EXP1/params.yaml:107-129)
+PRESETS = dict(
+    V=dict(depths=[2, 2, 9, 2], dims=96, drop_path_rate=0.2, patch_size=4, in_chans=3, ssm_d_state=16, ssm_ratio=2.0,
+           ssm_dt_rank="auto", ssm_act_layer="silu", ssm_conv=3, ssm_conv_bias=True, ssm_init="v0", forward_type="v0",
+           mlp_ratio=0.0, downsample_version="v1", patchembed_version="v1", norm_layer="ln"),
+    E=dict(depths=[2, 2, 2, 2], dims=96, drop_path_rate=0.2, patch_size=4, in_chans=3, ssm_d_state=1, ssm_ratio=1.0,
+           ssm_dt_rank="auto", ssm_act_layer="silu", ssm_conv=3, ssm_conv_bias=False, ssm_init="v0",
+           forward_type="v05_noz", mlp_ratio=4.0, downsample_version="v3", patchembed_version="v2", norm_layer="ln"),
+)
+
+
+def build_vssm(preset_or_kwargs) -> VSSM:
+    kw = PRESETS[preset_or_kwargs] if isinstance(preset_or_kwargs, str) else dict(preset_or_kwargs)
+    return VSSM(**kw)

@@ -1,0 +1,204 @@
+"""XPoint model (VMamba encoder + detector / descriptor heads) and the batched pair pipeline.
+
+``XPoint`` mirrors xpoint/models/XPoint.py for the configuration the north star names -- VMamba encoder,
+``multispectral: false``, descriptor head on, homography head off (it only works at 256x256):
+same ``XPoint(config)`` constructor, ``takes_pair()``, ``forward(data)`` output structure (tuple of dicts with
+``prob, logits, desc, encoder_output`` when ``takes_pair`` -- XPoint.py:181-214,283-323) and the same state_dict
+keys, so reference checkpoints load with ``load_state_dict``.
+
+``PairPipeline`` is the evaluation tail (xpoint/utils/evaluation.py:229-301) without its per-sample Python loop
+and device<->host copies: NMS + top-k + raster-order keypoints, bilinear descriptor sampling and mutual-NN
+matching for the whole batch on the GPU.
+"""
+from __future__ import annotations
+
+import contextlib
+import copy
+from typing import NamedTuple, Optional
+
+import torch
+import torch.nn as nn
+
+from . import postprocess as pp
+from .vmamba import PRESETS, VSSM
+
+_VSSM_KEYS = dict(PATCH_SIZE="patch_size", IN_CHANS="in_chans", DEPTHS="depths", EMBED_DIM="dims", SSM_D_STATE="ssm_d_state",
+                  SSM_RATIO="ssm_ratio", SSM_DT_RANK="ssm_dt_rank", SSM_ACT_LAYER="ssm_act_layer", SSM_CONV="ssm_conv",
+                  SSM_CONV_BIAS="ssm_conv_bias", SSM_DROP_RATE="ssm_drop_rate", SSM_INIT="ssm_init",
+                  SSM_FORWARDTYPE="forward_type", MLP_RATIO="mlp_ratio", MLP_ACT_LAYER="mlp_act_layer",
+                  MLP_DROP_RATE="mlp_drop_rate", PATCH_NORM="patch_norm", NORM_LAYER="norm_layer", DOWNSAMPLE="downsample_version",
+                  PATCHEMBED="patchembed_version", POSEMBED="posembed", GMLP="gmlp")
+# defaults of vmamba_src/MYCONFIG.py:72-97
+_VSSM_DEFAULTS = dict(patch_size=4, in_chans=3, depths=[2, 2, 9, 2], dims=96, ssm_d_state=16, ssm_ratio=2.0, ssm_dt_rank="auto",
+                      ssm_act_layer="silu", ssm_conv=3, ssm_conv_bias=True, ssm_drop_rate=0.0, ssm_init="v0", forward_type="v2",
+                      mlp_ratio=4.0, mlp_act_layer="gelu", mlp_drop_rate=0.0, patch_norm=True, norm_layer="ln",
+                      downsample_version="v2", patchembed_version="v2", posembed=False, gmlp=False)
+
+
+def _dict_update(d, u):  # xpoint/utils/utils.py:73-89
+    for k, v in u.items():
+        if isinstance(v, dict):
+            d[k] = _dict_update(d.get(k, {}) if isinstance(d.get(k, {}), dict) else {}, v)
+        else:
+            d[k] = v
+    return d
+
+
+def vssm_kwargs_from_config(model_parameters: dict) -> dict:
+    """Translate the YAML tree the reference feeds to MYCONFIG.get_config (params.yaml:107-129) into VSSM kwargs."""
+    kw = dict(_VSSM_DEFAULTS)
+    model = (model_parameters or {}).get("MODEL", {})
+    for k, v in model.get("VSSM", {}).items():
+        if k in _VSSM_KEYS:
+            kw[_VSSM_KEYS[k]] = v
+    kw["drop_path_rate"] = model.get("DROP_PATH_RATE", 0.1)
+    if kw["ssm_dt_rank"] != "auto":
+        kw["ssm_dt_rank"] = int(kw["ssm_dt_rank"])
+    return kw
+
+
+class XPoint(nn.Module):
+    default_config = {
+        "multispectral": False, "descriptor_head": True, "intepolation_mode": "bilinear", "descriptor_size": 256,
+        "normalize_descriptors": True, "final_batchnorm": True, "reflection_pad": True, "bn_first": False,
+        "double_convolution": True, "channel_version": 0, "verbose": False, "mixed_precision": False,
+        "force_return_logits": False, "takes_pair": False,
+        "homography_regression_head": {"check": False, "type": "RegNet"},
+        "use_attention": {"check": True, "type": "VMamba", "height": 256, "width": 256, "preset": "E",
+                          "model_parameters": None},
+    }
+
+    def __init__(self, config=None):
+        super().__init__()
+        self.config = _dict_update(copy.deepcopy(self.default_config), config or {})
+        c = self.config
+        if c["multispectral"]:
+            raise NotImplementedError("multispectral (two encoders) is not part of the accelerated path")
+        if c["homography_regression_head"]["check"]:
+            raise NotImplementedError("the RegNet homography head only works at 256x256 and is disabled at the benchmark "
+                                      "sizes (configs/cipdp.yaml:48); it is not built")
+        ua = c["use_attention"]
+        if not ua["check"] or ua["type"] != "VMamba":
+            raise NotImplementedError("only the VMamba encoder is built (use_attention.type == 'VMamba')")
+        if ua.get("model_parameters"):
+            kw = vssm_kwargs_from_config(ua["model_parameters"])
+        else:
+            kw = dict(PRESETS[ua.get("preset", "E")])
+        self.encoder = VSSM(**kw)
+        embed = kw["dims"] if isinstance(kw["dims"], int) else kw["dims"][0]
+        self.n_channels = [1, 64, 64, 128, embed // 2]          # XPoint.py:96,436
+        self.head_channels = 256
+        self.encoder_downsample_ratio = 8
+        pad = nn.ReflectionPad2d if c["reflection_pad"] else nn.ZeroPad2d
+        self.detector_head_last_dim = self.encoder_downsample_ratio ** 2 + 1
+
+        def nonlin(n):
+            return (nn.BatchNorm2d(n), nn.ReLU(True)) if c["bn_first"] else (nn.ReLU(True), nn.BatchNorm2d(n))
+
+        det = [pad(1), nn.Conv2d(self.n_channels[4], self.head_channels, 3), *nonlin(self.head_channels),
+               nn.Conv2d(self.head_channels, self.detector_head_last_dim, 1)]
+        if c["final_batchnorm"]:
+            det.append(nn.BatchNorm2d(self.detector_head_last_dim))
+        self.detector_head_convolutions = nn.Sequential(*det)
+        if c["descriptor_head"]:
+            desc = [pad(1), nn.Conv2d(self.n_channels[4], self.head_channels, 3), *nonlin(self.head_channels),
+                    nn.Conv2d(self.head_channels, c["descriptor_size"], 1)]
+            if c["final_batchnorm"]:
+                desc.append(nn.BatchNorm2d(c["descriptor_size"]))
+            self.descriptor_head_convolutions = nn.Sequential(*desc)
+
+    def takes_pair(self):
+        return self.config["takes_pair"]
+
+    def get_encoder_downsample_ratio(self):
+        return self.encoder_downsample_ratio
+
+    def set_force_return_logits(self, value):
+        if not isinstance(value, bool):
+            raise ValueError("set_force_return_logits: The input value needs to be a bool")
+        self.config["force_return_logits"] = value
+
+    # XPoint.py:348-360
+    def detector_head(self, x):
+        logits = self.detector_head_convolutions(x)
+        if self.training or self.config["force_return_logits"]:
+            return None, logits.to(torch.float)
+        return pp.detector_post(logits, self.encoder_downsample_ratio), None
+
+    # XPoint.py:362-371
+    def descriptor_head(self, x):
+        x = self.descriptor_head_convolutions(x)
+        if self.config["normalize_descriptors"]:
+            return pp.normalize_descriptors(x)
+        return x.to(torch.float)
+
+    def forward_impl(self, data):  # XPoint.py:283-323
+        x = self.encoder(data["image"])
+        out = {"prob": None, "logits": None}
+        encoder_output = x.clone().detach()
+        out["prob"], out["logits"] = self.detector_head(x)
+        if self.config["descriptor_head"]:
+            out["desc"] = self.descriptor_head(x)
+        out["encoder_output"] = encoder_output
+        return out
+
+    def forward(self, data):  # XPoint.py:181-214
+        ctx = torch.autocast("cuda", dtype=torch.float16) if self.config["mixed_precision"] else contextlib.nullcontext()
+        with ctx:
+            if not self.takes_pair():
+                return self.forward_impl(data)
+            pred_optical = self.forward_impl(data["optical"])
+            pred_thermal = self.forward_impl(data["thermal"])
+            return pred_optical, pred_thermal, None
+
+    def forward_pair_batched(self, optical: torch.Tensor, thermal: torch.Tensor):
+        """Same weights serve both spectra (multispectral=False), so the two encoder passes of XPoint.forward
+        (XPoint.py:187-188) run as one 2B batch.  Returns (pred_optical, pred_thermal) dicts."""
+        Bn = optical.shape[0]
+        ctx = torch.autocast("cuda", dtype=torch.float16) if self.config["mixed_precision"] else contextlib.nullcontext()
+        with ctx:
+            out = self.forward_impl({"image": torch.cat([optical, thermal], 0)})
+        first = {k: (v[:Bn] if v is not None else None) for k, v in out.items()}
+        second = {k: (v[Bn:] if v is not None else None) for k, v in out.items()}
+        return first, second
+
+
+class PairResult(NamedTuple):
+    kp_optical: torch.Tensor      # (B, k, 2) int32 (y, x)
+    kp_thermal: torch.Tensor
+    n_optical: torch.Tensor       # (B,) int32
+    n_thermal: torch.Tensor
+    desc_optical: torch.Tensor    # (B, k, 256) fp32, zero rows past n
+    desc_thermal: torch.Tensor
+    match_idx: torch.Tensor       # (B, k) int32, thermal keypoint index matched to optical keypoint i, or -1
+    match_dist: torch.Tensor      # (B, k) fp32
+    n_matches: torch.Tensor       # (B,) int32
+
+
+class PairPipeline:
+    """net(data) -> box_nms -> nonzero -> interpolate_descriptors x2 -> get_matches, batched on the GPU
+    (xpoint/utils/evaluation.py:229-301 with configs/cipdp.yaml:52-55: nms 8, detection_threshold 0.015)."""
+
+    def __init__(self, net: Optional[XPoint], nms=8, detection_threshold=0.015, iou=0.1, keep_top_k=4096,
+                 use_tensor_cores=True):
+        self.net = net
+        self.nms, self.thr, self.iou, self.topk = nms, detection_threshold, iou, keep_top_k
+        self.use_tensor_cores = use_tensor_cores
+
+    def tail(self, prob_o, prob_t, desc_o, desc_t) -> PairResult:
+        """prob (B,1,H,W) fp32; desc (B,256,Hc,Wc) fp32 -> keypoints, descriptors and mutual matches."""
+        B, _, H, W = prob_o.shape
+        prob = torch.cat([prob_o, prob_t], 0).reshape(2 * B, H, W)
+        kps = pp.nms_keypoints(prob, self.nms, self.thr, self.iou, self.topk, kp_threshold=self.thr, capacity=self.topk,
+                               want_map=False)
+        count = torch.clamp(kps.count, max=self.topk)
+        desc = torch.cat([desc_o, desc_t], 0)
+        d = pp.sample_descriptors(kps.keypoints, count, desc, H, W)
+        m = pp.mnn_match(d[:B], d[B:], count[:B], count[B:], use_tensor_cores=self.use_tensor_cores)
+        return PairResult(kps.keypoints[:B], kps.keypoints[B:], count[:B], count[B:], d[:B], d[B:], m.match_idx,
+                          m.match_dist, m.count)
+
+    @torch.no_grad()
+    def __call__(self, optical: torch.Tensor, thermal: torch.Tensor) -> PairResult:
+        po, pt = self.net.forward_pair_batched(optical, thermal)
+        return self.tail(po["prob"], pt["prob"], po["desc"], pt["desc"])

@@ -136,10 +136,25 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
-// softplus(beta=1, threshold=20) as torch / the reference kernel define it
-// (csms6s.py:49-50, selective_scan_fwd_kernel_oflex.cuh:124-127).  log1pf keeps the small-delta regime
-// (dt in [1e-3, 0.1] after softplus, VMamba.py:181-186) accurate to fp32 rounding.
-__device__ __forceinline__ float softplus_f(float x) { return x > 20.0f ? x : log1pf(__expf(x)); }
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// softplus(beta=1, threshold=20) as torch / the reference kernel define it (csms6s.py:49-50,
+// selective_scan_fwd_kernel_oflex.cuh:124-127): x > 20 ? x : log1p(exp(x)).  Branch-free, 2 MUFU + ~10 FP32 ops
+// (libdevice log1pf costs ~35 instructions and two branches):  e = exp(x);
+//   e <  1/16: log1p(e) = e - e^2/2 + e^3/3 - e^4/4 + e^5/5       (truncation e^5/6 < 1.6e-7 relative)
+//   e >= 1/16: log1p(e) = ln2 * lg2(1 + e)                          (lg2.approx abs error 2^-22 on >= 0.087)
+// The series branch keeps the small-delta regime (dt in [1e-3, 0.1], VMamba.py:181-186) at fp32 accuracy.
+__device__ __forceinline__ float softplus_f(float x) {
+    const float e = ex2_approx(x * kLog2e);
+    const float small = e * fmaf(e, fmaf(e, fmaf(e, fmaf(e, 0.2f, -0.25f), 0.33333334f), -0.5f), 1.0f);
+    const float big = lg2_approx(1.0f + e) * kLn2;
+    const float r = e < 0.0625f ? small : big;
+    return x > 20.0f ? x : r;
+}
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
@@ -199,6 +214,11 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                  :: "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
+}
+// 1-D bulk async copy global -> shared (UBLKCP), completion on mbarrier.  dst/src/bytes: multiples of 16.
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void tma_store_wait_read() {

@@ -124,41 +124,29 @@ __global__ void __launch_bounds__(GEN_WARPS * 32) scan_generic_kernel(const Scan
 // ============================================================================================
 // lanes kernel (dstate 1 | 2)
 // ============================================================================================
+// Per-warp software pipeline, no CTA-wide synchronisation:
+//   * lane 0 streams the next LN_STAGES (row, step) items with 1-D bulk async copies (cp.async.bulk -> UBLKCP,
+//     the TMA engine) into a per-warp shared-memory ring; completion is tracked by mbarriers, so the loads cost
+//     no registers and no scoreboard slots (a register prefetch aliased a scoreboard slot with the first SHFL of
+//     the next iteration and serialised the pipeline -- profiles/r1_scan_n1_v1.md);
+//   * every item is 256 consecutive tokens of one channel row (1 KiB fp32 per tensor): long DRAM bursts;
+//   * B/C chunks are loaded once per step into a double buffer and reused by the RW rows of the warp;
+//   * lanes read 8 tokens each (2 x LDS.128, conflict-free), scan them in registers, and the 32 lane chunks are
+//     combined with a warp-shuffle prefix scan of the affine maps h -> P*h + S; y leaves through 128-bit stores.
 constexpr int LN_WARPS = 4;
-constexpr int LN_C = 8;  // tokens per lane per step -> 256-token steps
+constexpr int LN_C = 8;        // tokens per lane per step -> 256-token steps
+constexpr int LN_STAGES = 4;   // ring depth (items in flight per warp)
 
-template <typename IN_T> struct RawVec;  // LN_C tokens of IN_T as raw 128-bit words
-template <> struct RawVec<float> { uint4 v[2]; };
-template <> struct RawVec<__half> { uint4 v[1]; };
-template <> struct RawVec<__nv_bfloat16> { uint4 v[1]; };
-
-template <typename IN_T> __device__ __forceinline__ void raw_load_stream(RawVec<IN_T>& r, const IN_T* p) {
-    constexpr int NV = sizeof(IN_T) * LN_C / 16;
-#pragma unroll
-    for (int i = 0; i < NV; ++i)
-        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                     : "=r"(r.v[i].x), "=r"(r.v[i].y), "=r"(r.v[i].z), "=r"(r.v[i].w)
-                     : "l"(reinterpret_cast<const uint4*>(p) + i));
+template <typename IN_T> __device__ __forceinline__ void lds_tokens8(const uint8_t* p, float (&f)[LN_C]);
+template <> __device__ __forceinline__ void lds_tokens8<float>(const uint8_t* p, float (&f)[LN_C]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 16);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
-template <typename IN_T> __device__ __forceinline__ void raw_load_cached(RawVec<IN_T>& r, const IN_T* p) {
-    constexpr int NV = sizeof(IN_T) * LN_C / 16;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) r.v[i] = __ldg(reinterpret_cast<const uint4*>(p) + i);
+template <> __device__ __forceinline__ void lds_tokens8<__half>(const uint8_t* p, float (&f)[LN_C]) {
+    VecIO<__half, 8>::widen(*reinterpret_cast<const uint4*>(p), f);
 }
-template <typename IN_T> __device__ __forceinline__ void raw_zero(RawVec<IN_T>& r) {
-    constexpr int NV = sizeof(IN_T) * LN_C / 16;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) r.v[i] = make_uint4(0, 0, 0, 0);
-}
-__device__ __forceinline__ void raw_widen(const RawVec<float>& r, float (&f)[LN_C]) {
-    f[0] = __uint_as_float(r.v[0].x); f[1] = __uint_as_float(r.v[0].y);
-    f[2] = __uint_as_float(r.v[0].z); f[3] = __uint_as_float(r.v[0].w);
-    f[4] = __uint_as_float(r.v[1].x); f[5] = __uint_as_float(r.v[1].y);
-    f[6] = __uint_as_float(r.v[1].z); f[7] = __uint_as_float(r.v[1].w);
-}
-__device__ __forceinline__ void raw_widen(const RawVec<__half>& r, float (&f)[LN_C]) { VecIO<__half, 8>::widen(r.v[0], f); }
-__device__ __forceinline__ void raw_widen(const RawVec<__nv_bfloat16>& r, float (&f)[LN_C]) {
-    VecIO<__nv_bfloat16, 8>::widen(r.v[0], f);
+template <> __device__ __forceinline__ void lds_tokens8<__nv_bfloat16>(const uint8_t* p, float (&f)[LN_C]) {
+    VecIO<__nv_bfloat16, 8>::widen(*reinterpret_cast<const uint4*>(p), f);
 }
 
 template <typename OUT_T> __device__ __forceinline__ void store_vec8(OUT_T* p, const float (&y)[LN_C]);
@@ -172,10 +160,28 @@ template <> __device__ __forceinline__ void store_vec8<__nv_bfloat16>(__nv_bfloa
     VecIO<__nv_bfloat16, 8>::store(p, y);
 }
 
+template <int NST, typename IN_T, bool HAS_Z> struct LanesCfg {
+    static constexpr int CHUNK = 32 * LN_C * (int)sizeof(IN_T);        // bytes of one 256-token chunk
+    static constexpr int ITEM = CHUNK * (HAS_Z ? 3 : 2);                // u, delta [, z]
+    static constexpr int BC = 2 * NST * CHUNK;                          // B rows then C rows
+    static constexpr int WARP_BYTES = LN_STAGES * ITEM + 2 * BC;
+    static constexpr int NBARS = LN_STAGES + 2;
+    static constexpr int SMEM = LN_WARPS * (WARP_BYTES + NBARS * 8) + 16;
+};
+
 template <int NST, typename IN_T, typename OUT_T, bool HAS_Z>
 __global__ void __launch_bounds__(LN_WARPS * 32) scan_lanes_kernel(const ScanParams p) {
-    const int lane = threadIdx.x & 31;
-    const int64_t wid = (int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+    using Cfg = LanesCfg<NST, IN_T, HAS_Z>;
+    constexpr int TOK = 32 * LN_C;
+    extern __shared__ uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 15) & ~uintptr_t(15));
+    uint8_t* ring = base + warp * Cfg::WARP_BYTES;
+    uint8_t* bcbuf = ring + LN_STAGES * Cfg::ITEM;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + LN_WARPS * Cfg::WARP_BYTES) + warp * Cfg::NBARS;
+    uint64_t* bcbars = bars + LN_STAGES;
+
+    const int64_t wid = (int64_t)blockIdx.x * LN_WARPS + warp;
     const int RW = p.rows_per_warp;
     const int64_t Dg = p.dim / p.groups;
     const int64_t rb_per_group = (Dg + RW - 1) / RW;
@@ -185,13 +191,14 @@ __global__ void __launch_bounds__(LN_WARPS * 32) scan_lanes_kernel(const ScanPar
     const int64_t b = wid / (rb_per_group * p.groups);
     const int64_t d0 = g * Dg + rb * RW;
     const int nrows = (int)min((int64_t)RW, Dg - rb * RW);
+    const int S = min(LN_STAGES, nrows);     // ring depth actually used (keeps the B/C double buffer safe)
 
     const IN_T* ub = (const IN_T*)p.u + b * p.u_bs + d0 * p.u_ds;
     const IN_T* db = (const IN_T*)p.delta + b * p.dl_bs + d0 * p.dl_ds;
     const IN_T* zb = HAS_Z ? (const IN_T*)p.z + b * p.z_bs + d0 * p.z_ds : nullptr;
     const IN_T* Bb = (const IN_T*)p.Bm + b * p.B_bs + g * p.B_gs;
     const IN_T* Cb = (const IN_T*)p.Cm + b * p.C_bs + g * p.C_gs;
-    OUT_T* ob = (OUT_T*)p.out + b * p.o_bs + d0 * p.o_ds;
+    OUT_T* ob = (OUT_T*)p.out + b * p.o_bs + d0 * p.o_ds + lane * LN_C;
 
     // per-row constants live in lane r (r < nrows <= 32); broadcast with shuffles inside the row loop
     float A2_l[NST], carry_l[NST], bias_l = 0.0f, D_l = 0.0f;
@@ -204,92 +211,98 @@ __global__ void __launch_bounds__(LN_WARPS * 32) scan_lanes_kernel(const ScanPar
         D_l = p.D ? p.D[d0 + lane] : 0.0f;
     }
 
-    const int64_t nsteps = (p.L + 32 * LN_C - 1) / (32 * LN_C);
-    const int64_t total = nsteps * nrows;
-    // prefetch pipeline over the flattened (step, row) index
-    RawVec<IN_T> u_nx, d_nx, z_nx;
-    {
-        const int64_t l0 = (int64_t)lane * LN_C;
-        if (l0 < p.L) {
-            raw_load_stream(u_nx, ub + l0);
-            raw_load_stream(d_nx, db + l0);
-            if (HAS_Z) raw_load_stream(z_nx, zb + l0);
-        } else {
-            raw_zero(u_nx); raw_zero(d_nx);
-            if (HAS_Z) raw_zero(z_nx);
-        }
-    }
-    float Bv[NST][LN_C], Cv[NST][LN_C];
-    int r = 0;
-    int64_t step = 0;
-    for (int64_t it = 0; it < total; ++it) {
-        const int64_t l0 = step * (32 * LN_C) + (int64_t)lane * LN_C;
-        const bool ok = l0 < p.L;  // L % LN_C-vector alignment is guaranteed by the host: chunks are all-or-nothing
-        if (r == 0) {
+    const int nsteps = (int)((p.L + TOK - 1) / TOK);
+    const int total = nsteps * nrows;
+    // producer cursor (lane 0): next item to issue
+    int is = 0, ir = 0, islot = 0;
+    auto issue = [&]() {
+        const int64_t t0 = (int64_t)is * TOK;
+        const uint32_t bytes = (uint32_t)(min((int64_t)TOK, p.L - t0) * (int64_t)sizeof(IN_T));
+        uint8_t* dst = ring + islot * Cfg::ITEM;
+        mbar_arrive_expect_tx(&bars[islot], bytes * (HAS_Z ? 3 : 2));
+        bulk_load(dst, ub + ir * p.u_ds + t0, bytes, &bars[islot]);
+        bulk_load(dst + Cfg::CHUNK, db + ir * p.dl_ds + t0, bytes, &bars[islot]);
+        if (HAS_Z) bulk_load(dst + 2 * Cfg::CHUNK, zb + ir * p.z_ds + t0, bytes, &bars[islot]);
+        if (ir == 0) {
+            uint8_t* bc = bcbuf + (is & 1) * Cfg::BC;
+            mbar_arrive_expect_tx(&bcbars[is & 1], bytes * 2 * NST);
 #pragma unroll
             for (int n = 0; n < NST; ++n) {
-                if (ok) {
-                    RawVec<IN_T> t;
-                    raw_load_cached(t, Bb + n * p.B_ss + l0); raw_widen(t, Bv[n]);
-                    raw_load_cached(t, Cb + n * p.C_ss + l0); raw_widen(t, Cv[n]);
-                } else {
+                bulk_load(bc + n * Cfg::CHUNK, Bb + n * p.B_ss + t0, bytes, &bcbars[is & 1]);
+                bulk_load(bc + (NST + n) * Cfg::CHUNK, Cb + n * p.C_ss + t0, bytes, &bcbars[is & 1]);
+            }
+        }
+        if (++ir == nrows) { ir = 0; ++is; }
+        if (++islot == S) islot = 0;
+    };
+    if (lane == 0) {
+        for (int s = 0; s < Cfg::NBARS; ++s) mbar_init(&bars[s], 1);
+        fence_mbar_init();
+        fence_proxy_async();
+        for (int s = 0; s < S && s < total; ++s) issue();
+    }
+    __syncwarp();
+
+    float Bv[NST][LN_C], Cv[NST][LN_C];
+    int r = 0, step = 0, slot = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < total; ++it) {
+        const int64_t l0 = (int64_t)step * TOK + lane * LN_C;
+        const bool ok = l0 < p.L;   // L % vector width == 0 is guaranteed by the host: lane chunks are all-or-nothing
+        if (r == 0) {
+            mbar_wait(&bcbars[step & 1], (uint32_t)((step >> 1) & 1));
+            const uint8_t* bc = bcbuf + (step & 1) * Cfg::BC + lane * (LN_C * (int)sizeof(IN_T));
 #pragma unroll
-                    for (int j = 0; j < LN_C; ++j) { Bv[n][j] = 0.0f; Cv[n][j] = 0.0f; }
-                }
+            for (int n = 0; n < NST; ++n) {
+                lds_tokens8<IN_T>(bc + n * Cfg::CHUNK, Bv[n]);
+                lds_tokens8<IN_T>(bc + (NST + n) * Cfg::CHUNK, Cv[n]);
             }
         }
-        // current row's data, then kick off the next (row, step)
+        mbar_wait(&bars[slot], phase);
+        const uint8_t* item = ring + slot * Cfg::ITEM + lane * (LN_C * (int)sizeof(IN_T));
         float uv[LN_C], dv[LN_C], zv[LN_C];
-        raw_widen(u_nx, uv);
-        raw_widen(d_nx, dv);
-        if (HAS_Z) raw_widen(z_nx, zv);
-        {
-            int rn = r + 1; int64_t sn = step;
-            if (rn == nrows) { rn = 0; ++sn; }
-            const int64_t ln = sn * (32 * LN_C) + (int64_t)lane * LN_C;
-            if (it + 1 < total && ln < p.L) {
-                raw_load_stream(u_nx, ub + rn * p.u_ds + ln);
-                raw_load_stream(d_nx, db + rn * p.dl_ds + ln);
-                if (HAS_Z) raw_load_stream(z_nx, zb + rn * p.z_ds + ln);
-            } else {
-                raw_zero(u_nx); raw_zero(d_nx);
-                if (HAS_Z) raw_zero(z_nx);
-            }
-        }
+        lds_tokens8<IN_T>(item, uv);
+        lds_tokens8<IN_T>(item + Cfg::CHUNK, dv);
+        if (HAS_Z) lds_tokens8<IN_T>(item + 2 * Cfg::CHUNK, zv);
+        __syncwarp();                                   // every lane has drained this slot
+        if (lane == 0 && it + S < total) issue();       // refill it with item it + S
+        if (++slot == S) { slot = 0; phase ^= 1; }
+
         const float bias = __shfl_sync(0xffffffffu, bias_l, r);
         const float Dv = __shfl_sync(0xffffffffu, D_l, r);
         float y[LN_C];
 #pragma unroll
         for (int j = 0; j < LN_C; ++j) {
-            dv[j] = ok ? delta_act(dv[j], bias, p.softplus) : 0.0f;  // 0 -> a = 1, b = 0: identity step
+            const float dl = delta_act(dv[j], bias, p.softplus);
+            dv[j] = ok ? dl : 0.0f;                     // 0 -> a = 1, b = 0: identity step past the end
             y[j] = Dv * uv[j];
-            uv[j] *= dv[j];                                           // delta * u
+            uv[j] = ok ? uv[j] * dl : 0.0f;             // delta * u
         }
 #pragma unroll
         for (int n = 0; n < NST; ++n) {
             const float A2 = __shfl_sync(0xffffffffu, A2_l[n], r);
             const float hc = __shfl_sync(0xffffffffu, carry_l[n], r);
             float hl[LN_C], pl[LN_C];
-            float P = 1.0f, S = 0.0f;
+            float P = 1.0f, S_ = 0.0f;
 #pragma unroll
             for (int j = 0; j < LN_C; ++j) {
                 const float a = ex2_approx(dv[j] * A2);
-                S = fmaf(a, S, uv[j] * Bv[n][j]);
+                S_ = fmaf(a, S_, ok ? uv[j] * Bv[n][j] : 0.0f);
                 P *= a;
-                hl[j] = S; pl[j] = P;
+                hl[j] = S_; pl[j] = P;
             }
             // warp-level inclusive scan of the affine maps h -> P*h + S across the 32 lane chunks
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const float Pp = __shfl_up_sync(0xffffffffu, P, o), Sp = __shfl_up_sync(0xffffffffu, S, o);
-                if (lane >= o) { S = fmaf(P, Sp, S); P *= Pp; }
+                const float Pp = __shfl_up_sync(0xffffffffu, P, o), Sp = __shfl_up_sync(0xffffffffu, S_, o);
+                if (lane >= o) { S_ = fmaf(P, Sp, S_); P *= Pp; }
             }
-            float Pe = __shfl_up_sync(0xffffffffu, P, 1), Se = __shfl_up_sync(0xffffffffu, S, 1);
+            float Pe = __shfl_up_sync(0xffffffffu, P, 1), Se = __shfl_up_sync(0xffffffffu, S_, 1);
             if (lane == 0) { Pe = 1.0f; Se = 0.0f; }
             const float hin = fmaf(Pe, hc, Se);
 #pragma unroll
-            for (int j = 0; j < LN_C; ++j) y[j] = fmaf(fmaf(pl[j], hin, hl[j]), Cv[n][j], y[j]);
-            const float hend = __shfl_sync(0xffffffffu, fmaf(P, hc, S), 31);
+            for (int j = 0; j < LN_C; ++j) y[j] = fmaf(fmaf(pl[j], hin, hl[j]), ok ? Cv[n][j] : 0.0f, y[j]);
+            const float hend = __shfl_sync(0xffffffffu, fmaf(P, hc, S_), 31);
             if (lane == r) carry_l[n] = hend;
         }
         if (ok) {
@@ -297,7 +310,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) scan_lanes_kernel(const ScanPar
 #pragma unroll
                 for (int j = 0; j < LN_C; ++j) y[j] *= silu_f(zv[j]);
             }
-            store_vec8<OUT_T>(ob + r * p.o_ds + l0, y);
+            store_vec8<OUT_T>(ob + r * p.o_ds + (int64_t)step * TOK, y);
         }
         if (++r == nrows) { r = 0; ++step; }
     }
@@ -491,8 +504,15 @@ template <int NST, typename IN_T, typename OUT_T> static int launch_lanes(ScanPa
     p.rows_per_warp = rw;
     const int64_t warps = p.batch * p.groups * ceil_div(Dg, rw);
     const unsigned grid = (unsigned)ceil_div(warps, LN_WARPS);
-    if (p.z) scan_lanes_kernel<NST, IN_T, OUT_T, true><<<grid, LN_WARPS * 32, 0, st>>>(p);
-    else scan_lanes_kernel<NST, IN_T, OUT_T, false><<<grid, LN_WARPS * 32, 0, st>>>(p);
+    if (p.z) {
+        constexpr int smem = LanesCfg<NST, IN_T, true>::SMEM;
+        XP_CUDA_OK(cudaFuncSetAttribute(scan_lanes_kernel<NST, IN_T, OUT_T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        scan_lanes_kernel<NST, IN_T, OUT_T, true><<<grid, LN_WARPS * 32, smem, st>>>(p);
+    } else {
+        constexpr int smem = LanesCfg<NST, IN_T, false>::SMEM;
+        XP_CUDA_OK(cudaFuncSetAttribute(scan_lanes_kernel<NST, IN_T, OUT_T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        scan_lanes_kernel<NST, IN_T, OUT_T, false><<<grid, LN_WARPS * 32, smem, st>>>(p);
+    }
     XP_LAUNCH_CHECK("scan_lanes_kernel");
     return XP_OK;
 }

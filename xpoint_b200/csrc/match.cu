@@ -19,7 +19,8 @@ namespace xp {
 
 int mnn_argmin_tc(const float* X, const float* Y, const int32_t* nx, const int32_t* ny, int64_t P, int64_t x_stride,
                   int64_t y_stride, int64_t C, const float* xnorm, const float* ynorm, int32_t* nn_x, int32_t* nn_y,
-                  unsigned long long* row_keys, unsigned long long* col_keys, cudaStream_t st);
+                  void* split_ws, cudaStream_t st);
+int64_t mnn_tc_workspace_bytes(int64_t P, int64_t x_stride, int64_t y_stride, int64_t C);
 
 // ---------------------------------------------------------------------------------- row norms
 __global__ void __launch_bounds__(256) row_norm2_kernel(const float* __restrict__ X, float* __restrict__ out, int64_t rows,
@@ -151,11 +152,10 @@ __global__ void __launch_bounds__(256) mutual_kernel(const float* __restrict__ d
 
 using namespace xp;
 
-// workspace layout: [xnorm P*n1][ynorm P*n2][nn12 P*n1][nn21 P*n2][row_keys u64 P*n1][col_keys u64 P*n2]
+// workspace layout: [xnorm P*n1][ynorm P*n2][nn12 P*n1][nn21 P*n2][tf32 hi/lo copies of d1 and d2 (tensor-core path)]
 extern "C" int64_t xp_match_workspace_bytes(int64_t P, int64_t n1_stride, int64_t n2_stride, int64_t C) {
-    (void)C;
     const int64_t a = P * n1_stride, b = P * n2_stride;
-    return (a + b) * 4 * 2 + (a + b) * 8 + 256;
+    return (a + b) * 4 * 2 + 256 + mnn_tc_workspace_bytes(P, n1_stride, n2_stride, C);
 }
 
 extern "C" int xp_mnn_match(const float* d1, const float* d2, const int32_t* n1, const int32_t* n2, int64_t P,
@@ -180,8 +180,7 @@ extern "C" int xp_mnn_match(const float* d1, const float* d2, const int32_t* n1,
     float* ynorm = xnorm + a;
     int32_t* w12 = (int32_t*)(ynorm + b);
     int32_t* w21 = w12 + a;
-    unsigned long long* rkeys = (unsigned long long*)(((uintptr_t)(w21 + b) + 15) & ~(uintptr_t)15);
-    unsigned long long* ckeys = rkeys + a;
+    void* split_ws = (void*)(w21 + b);
     int32_t* o12 = nn12 ? nn12 : w12;
     int32_t* o21 = nn21 ? nn21 : w21;
     if (n2_stride == 0) {
@@ -196,7 +195,7 @@ extern "C" int xp_mnn_match(const float* d1, const float* d2, const int32_t* n1,
     row_norm2_kernel<<<(unsigned)ceil_div(b, 8), 256, 0, st>>>(d2, ynorm, b, (int)C);
     XP_LAUNCH_CHECK("row_norm2_kernel");
     if (use_tensor_cores) {
-        int rc = mnn_argmin_tc(d1, d2, n1, n2, P, n1_stride, n2_stride, C, xnorm, ynorm, o12, o21, rkeys, ckeys, st);
+        int rc = mnn_argmin_tc(d1, d2, n1, n2, P, n1_stride, n2_stride, C, xnorm, ynorm, o12, o21, split_ws, st);
         if (rc) return rc;
     } else {
         // rows with index >= n (per pair) are never written: pre-fill with -1

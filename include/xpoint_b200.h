@@ -123,6 +123,14 @@ XP_API int xp_merge_norm_gate(const void* ys, const float* gamma, const float* b
                        int64_t B, int64_t C, int64_t H, int64_t W, int32_t ys_dtype, int32_t out_dtype, float eps,
                        void* workspace, int64_t workspace_bytes, xp_stream_t stream);
 
+/* -- f2 (first "next" row): channel-last LayerNorm ---------------------------------------
+ * Replaces the nn.LayerNorm calls around the SS2D block (VSSBlock.norm / norm2, patch-embed and downsample norms:
+ * VMamba.py:1222-1234, :1405-1440).  x (rows, C) in in_dtype -> y (rows, C) in out_dtype; gamma/beta (C) fp32;
+ * fp32 statistics, biased variance, eps inside the square root (torch semantics).  C <= 1536.
+ */
+XP_API int xp_layer_norm(const void* x, const float* gamma, const float* beta, void* y, int64_t rows, int64_t C,
+                         int32_t in_dtype, int32_t out_dtype, float eps, xp_stream_t stream);
+
 /* -- a6: detector post ----------------------------------------------------------------
  * Replaces Softmax2d -> [:, :-1] -> PixelShuffle(r)   (XPoint.py:356-357).
  * logits (B, r*r+1, Hc, Wc) in `dtype` -> prob (B, 1, r*Hc, r*Wc) fp32.  r <= 8.

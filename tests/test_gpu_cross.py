@@ -101,3 +101,19 @@ def test_errors():
     with pytest.raises(RuntimeError):
         X.cross_scan_fn(torch.zeros(1, 2, 3, 4, device=DEV), scans=5)
     assert X.cross_scan_fn(torch.zeros(0, 2, 3, 4, device=DEV)).shape == (0, 4, 2, 12)
+
+
+@pytest.mark.parametrize("C", [48, 96, 192, 384, 768, 1536, 37])
+@pytest.mark.parametrize("dt_in,dt_out", [(torch.float32, torch.float32), (torch.float32, torch.float16),
+                                          (torch.float16, torch.float16), (torch.bfloat16, torch.float32)])
+def test_layer_norm(C, dt_in, dt_out):
+    """xp_layer_norm vs torch's fp32 LayerNorm on the same (pre-rounded) input."""
+    from xpoint_b200.cross_scan import layer_norm
+    g = torch.Generator().manual_seed(C)
+    x = (torch.randn(3, 17, 5, C, generator=g) * 2 + 0.5).to(dt_in)
+    w = 1 + 0.1 * torch.randn(C, generator=g)
+    b = 0.1 * torch.randn(C, generator=g)
+    ref = torch.nn.functional.layer_norm(x.float(), (C,), w, b, 1e-5)
+    out = layer_norm(x.to(DEV), w.to(DEV), b.to(DEV), 1e-5, dt_out)
+    assert out.dtype == dt_out and out.shape == x.shape
+    assert_close(out.float().cpu().numpy(), ref.numpy(), 1e-5 if dt_out == torch.float32 else 2e-3, f"layer_norm C={C}")

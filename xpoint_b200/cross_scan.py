@@ -131,3 +131,18 @@ def merge_norm_gate(ys: torch.Tensor, H: int, W: int, weight: torch.Tensor, bias
                                           _lib.stream_ptr(dev)))
     _lib.count_launches(3)
     return out
+
+
+def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5, out_dtype=None):
+    """LayerNorm over the last dimension of a channel-last tensor (xp_layer_norm)."""
+    dev = _lib.require_cuda(x, weight, bias)
+    x = x.contiguous()
+    C = x.shape[-1]
+    out = torch.empty(x.shape, dtype=out_dtype or x.dtype, device=dev)
+    if out.numel():
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().xp_layer_norm(_lib.ptr(x), _lib.ptr(weight.float().contiguous()),
+                                                _lib.ptr(bias.float().contiguous()), _lib.ptr(out), x.numel() // C, C,
+                                                _lib.dtype_code(x), _lib.dtype_code(out), float(eps), _lib.stream_ptr(dev)))
+        _lib.count_launches(1)
+    return out

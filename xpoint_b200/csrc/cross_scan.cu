@@ -315,3 +315,79 @@ extern "C" int xp_merge_norm_gate(const void* ys, const float* gamma, const floa
     set_error("xp_merge_norm_gate: unsupported dtype combination ys=%d out=%d", ys_dtype, out_dtype);
     return XP_ERR_INVALID_ARG;
 }
+
+// ================================================================================================
+// Channel-last LayerNorm over the last dimension (rows x C), fp32 statistics.
+// Replaces the nn.LayerNorm calls of VSSBlock / patch-embed / downsample (VMamba.py:1222-1234, :1405-1440):
+// token rows are short (C = 48..1536) and there are millions of them, so one warp per row with the row held
+// in registers (two-pass variance, exactly torch's definition) beats a block-per-row library kernel.
+// ================================================================================================
+namespace xp {
+template <typename TI, typename TO, int PER_LANE>
+__global__ void __launch_bounds__(256) layer_norm_kernel(const TI* __restrict__ x, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, TO* __restrict__ y, int64_t rows,
+                                                         int C, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const TI* xr = x + row * C;
+    float v[PER_LANE];
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < PER_LANE; ++i) {
+        const int c = lane + 32 * i;
+        v[i] = c < C ? to_f32(xr[c]) : 0.0f;
+        s += v[i];
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float ss = 0.0f;
+#pragma unroll
+    for (int i = 0; i < PER_LANE; ++i) {
+        const int c = lane + 32 * i;
+        const float d = c < C ? v[i] - mean : 0.0f;
+        ss += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / (float)C + eps);
+    TO* yr = y + row * C;
+#pragma unroll
+    for (int i = 0; i < PER_LANE; ++i) {
+        const int c = lane + 32 * i;
+        if (c < C) yr[c] = from_f32<TO>((v[i] - mean) * rstd * gamma[c] + beta[c]);
+    }
+}
+
+template <typename TI, typename TO> static int ln_launch(const void* x, const float* g, const float* b, void* y, int64_t rows,
+                                                         int C, float eps, cudaStream_t st) {
+    const unsigned grid = (unsigned)ceil_div(rows, 8);
+    const int per = (C + 31) / 32;
+#define XP_LN_CASE(P) layer_norm_kernel<TI, TO, P><<<grid, 256, 0, st>>>((const TI*)x, g, b, (TO*)y, rows, C, eps)
+    if (per <= 2) XP_LN_CASE(2);
+    else if (per <= 3) XP_LN_CASE(3);
+    else if (per <= 6) XP_LN_CASE(6);
+    else if (per <= 12) XP_LN_CASE(12);
+    else if (per <= 24) XP_LN_CASE(24);
+    else if (per <= 48) XP_LN_CASE(48);
+    else { set_error("xp_layer_norm: C must be <= 1536 (got %d)", C); return XP_ERR_INVALID_ARG; }
+#undef XP_LN_CASE
+    XP_LAUNCH_CHECK("layer_norm_kernel");
+    return XP_OK;
+}
+}  // namespace xp
+
+extern "C" int xp_layer_norm(const void* x, const float* gamma, const float* beta, void* y, int64_t rows, int64_t C,
+                             int32_t in_dtype, int32_t out_dtype, float eps, xp_stream_t stream) {
+    XP_REQUIRE(x && gamma && beta && y, "xp_layer_norm: NULL tensor pointer");
+    XP_REQUIRE(rows >= 0 && C > 0, "xp_layer_norm: bad shape");
+    if (rows == 0) return XP_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (in_dtype * 4 + out_dtype) {
+        case XP_F32 * 4 + XP_F32: return xp::ln_launch<float, float>(x, gamma, beta, y, rows, (int)C, eps, st);
+        case XP_F32 * 4 + XP_F16: return xp::ln_launch<float, __half>(x, gamma, beta, y, rows, (int)C, eps, st);
+        case XP_F32 * 4 + XP_BF16: return xp::ln_launch<float, __nv_bfloat16>(x, gamma, beta, y, rows, (int)C, eps, st);
+        case XP_F16 * 4 + XP_F16: return xp::ln_launch<__half, __half>(x, gamma, beta, y, rows, (int)C, eps, st);
+        case XP_F16 * 4 + XP_F32: return xp::ln_launch<__half, float>(x, gamma, beta, y, rows, (int)C, eps, st);
+        case XP_BF16 * 4 + XP_BF16: return xp::ln_launch<__nv_bfloat16, __nv_bfloat16>(x, gamma, beta, y, rows, (int)C, eps, st);
+        case XP_BF16 * 4 + XP_F32: return xp::ln_launch<__nv_bfloat16, float>(x, gamma, beta, y, rows, (int)C, eps, st);
+        default: xp::set_error("xp_layer_norm: unsupported dtype combination %d -> %d", in_dtype, out_dtype); return XP_ERR_INVALID_ARG;
+    }
+}

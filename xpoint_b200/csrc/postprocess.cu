@@ -163,41 +163,42 @@ __global__ void __launch_bounds__(NMS_THREADS) box_nms_kernel(const NmsParams p)
         __syncthreads();
         if (alive == 0) break;
         if (tid == 0) alive_s = 0;
-        // phase A: local maxima among undecided candidates become NEW
+        // phase A: an undecided candidate with no undecided higher-priority candidate in its footprint is kept (NEW).
+        // Early exit on the first better neighbour: O(1) expected work for the non-maxima of a dense map.
         for (int q = tid; q < HW; q += NMS_THREADS) {
             if (st[q] != ST_ALIVE) continue;
             const float s = prob[q];
             const int y = q / W, x = q - y * W;
             bool best = true;
-            for (int o = 0; o < n_offs && best; ++o) {
+            for (int o = 0; o < n_offs; ++o) {
                 const int yy = y + off_dy[o], xx = x + off_dx[o];
                 if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
                 const int r = yy * W + xx;
                 const uint8_t sr = st[r];
                 if (sr == ST_ALIVE || sr == ST_NEW) {   // NEW this round was ALIVE at round start
                     const float t = prob[r];
-                    if (t > s || (t == s && r < q)) best = false;
+                    if (t > s || (t == s && r < q)) { best = false; break; }
                 }
             }
             if (best) st[q] = ST_NEW;
         }
         __syncthreads();
-        // phase B: undecided candidates inside a NEW footprint are suppressed
-        int still = 0;
+        // phase B (scatter): every NEW pixel suppresses the undecided candidates in its footprint and becomes KEPT.
+        // Two NEW pixels are never inside each other's footprint, so NEW is never overwritten.
         for (int q = tid; q < HW; q += NMS_THREADS) {
-            if (st[q] != ST_ALIVE) continue;
+            if (st[q] != ST_NEW) continue;
             const int y = q / W, x = q - y * W;
-            bool dead = false;
-            for (int o = 0; o < n_offs && !dead; ++o) {
+            for (int o = 0; o < n_offs; ++o) {
                 const int yy = y + off_dy[o], xx = x + off_dx[o];
                 if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-                if (st[yy * W + xx] == ST_NEW) dead = true;
+                const int r = yy * W + xx;
+                if (st[r] == ST_ALIVE) st[r] = ST_NONE;
             }
-            if (dead) st[q] = ST_NONE; else ++still;
+            st[q] = ST_KEPT;
         }
         __syncthreads();
-        for (int q = tid; q < HW; q += NMS_THREADS)
-            if (st[q] == ST_NEW) st[q] = ST_KEPT;
+        int still = 0;
+        for (int q = tid; q < HW; q += NMS_THREADS) still += st[q] == ST_ALIVE;
         if (still) atomicAdd(&alive_s, still);
         __syncthreads();
     }
@@ -239,39 +240,46 @@ __global__ void __launch_bounds__(NMS_THREADS) box_nms_kernel(const NmsParams p)
         }
     }
 
-    // ---- dense output + raster-order compaction (chunked block scan keeps the order) ----
+    // ---- dense output + raster-order compaction: every thread owns a contiguous pixel range, one block scan
+    //      per quantity gives its output offset, so the order is the raster order ----
     float* out = p.out ? p.out + (int64_t)b * HW : nullptr;
     int32_t* kp = p.kp ? p.kp + (int64_t)b * p.kp_cap * 2 : nullptr;
-    int eq_seen = 0, kp_seen = 0;
-    for (int base = 0; base < HW; base += NMS_THREADS) {
-        const int q = base + tid;
-        bool kept = false, eq = false;
+    const int chunk = (HW + NMS_THREADS - 1) / NMS_THREADS;
+    const int q0 = min(tid * chunk, HW), q1 = min(q0 + chunk, HW);
+    int eq_before = 0;
+    if (need_eq >= 0) {
+        int eq_local = 0;
+        for (int q = q0; q < q1; ++q) eq_local += (st[q] == ST_KEPT && __float_as_uint(prob[q]) == thr_bits);
+        int tot;
+        eq_before = block_exclusive_scan(eq_local, scan_ws, tot);
+    }
+    // pass 1: decide + count keypoints in my range (state byte: KEPT -> KEPT if selected else NONE)
+    int kp_local = 0;
+    for (int q = q0; q < q1; ++q) {
+        bool kept = false;
         float s = 0.0f;
-        if (q < HW && st[q] == ST_KEPT) {
+        if (st[q] == ST_KEPT) {
             s = prob[q];
             const unsigned bits = __float_as_uint(s);
             if (need_eq < 0 || bits > thr_bits) kept = true;
-            else if (bits == thr_bits) eq = true;
+            else if (bits == thr_bits) { kept = eq_before < need_eq; ++eq_before; }
         }
-        if (need_eq >= 0) {
-            int tot;
-            const int rank = block_exclusive_scan(eq ? 1 : 0, scan_ws, tot);
-            if (eq && eq_seen + rank < need_eq) kept = true;
-            eq_seen += tot;
-        }
-        if (q < HW && out) out[q] = kept ? s : 0.0f;
-        if (kp || p.kp_count) {
-            const bool iskp = kept && s > p.kp_thr;
-            int tot;
-            const int rank = block_exclusive_scan(iskp ? 1 : 0, scan_ws, tot);
-            if (iskp && kp && kp_seen + rank < p.kp_cap) {
-                kp[2 * (kp_seen + rank)] = q / W;
-                kp[2 * (kp_seen + rank) + 1] = q % W;
-            }
-            kp_seen += tot;
-        }
+        st[q] = kept ? ST_KEPT : ST_NONE;
+        kp_local += kept && s > p.kp_thr;
     }
-    if (p.kp_count && tid == 0) p.kp_count[b] = kp_seen;
+    int kp_total = 0, kp_off = 0;
+    if (kp || p.kp_count) kp_off = block_exclusive_scan(kp_local, scan_ws, kp_total);
+    if (kp) {
+        for (int q = q0; q < q1; ++q)
+            if (st[q] == ST_KEPT && prob[q] > p.kp_thr) {
+                if (kp_off < p.kp_cap) { kp[2 * kp_off] = q / W; kp[2 * kp_off + 1] = q % W; }
+                ++kp_off;
+            }
+    }
+    if (p.kp_count && tid == 0) p.kp_count[b] = kp_total;
+    __syncthreads();
+    if (out)
+        for (int q = tid; q < HW; q += NMS_THREADS) out[q] = st[q] == ST_KEPT ? prob[q] : 0.0f;   // coalesced
 }
 
 // ================================================================================================

@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .cross_scan import cross_scan_fn, merge_norm_gate
+from .cross_scan import cross_scan_fn, layer_norm, merge_norm_gate
 from .selective_scan import selective_scan_fn
 
 
@@ -31,6 +31,23 @@ class Permute(nn.Module):
 
     def forward(self, x):
         return x.permute(*self.args)
+
+
+class LayerNorm(nn.LayerNorm):
+    """nn.LayerNorm with the same parameters / state_dict keys, forward on the xp_layer_norm kernel.
+
+    ``for_matmul``: the result only feeds a Linear, so under autocast it is written directly in the autocast
+    dtype (torch computes the norm in fp32 and lets the Linear cast it: same values, one pass less)."""
+
+    def __init__(self, normalized_shape, eps=1e-5, for_matmul=False):
+        super().__init__(normalized_shape, eps=eps)
+        self.for_matmul = for_matmul
+
+    def forward(self, x):
+        out_dtype = None
+        if torch.is_autocast_enabled():
+            out_dtype = torch.get_autocast_gpu_dtype() if self.for_matmul else torch.float32
+        return layer_norm(x, self.weight, self.bias, self.eps, out_dtype)
 
 
 class Mlp(nn.Module):  # VMamba.py:110-128 (channel-last only; XPoint never builds channel-first VSSMs)
@@ -52,7 +69,7 @@ class PatchMerging2D(nn.Module):  # VMamba.py:60-98, channel-last
         super().__init__()
         assert not channel_first
         self.reduction = nn.Linear(4 * dim, (2 * dim) if out_dim < 0 else out_dim, bias=False)
-        self.norm = norm_layer(4 * dim)
+        self.norm = LayerNorm(4 * dim, for_matmul=True)
 
     def forward(self, x):
         H, W, _ = x.shape[-3:]
@@ -209,12 +226,12 @@ class VSSBlock(nn.Module):  # VMamba.py:1153-1240
         self.ssm_branch = ssm_ratio > 0
         self.mlp_branch = mlp_ratio > 0
         if self.ssm_branch:
-            self.norm = norm_layer(hidden_dim)
+            self.norm = LayerNorm(hidden_dim, for_matmul=True)
             self.op = SS2D(d_model=hidden_dim, d_state=ssm_d_state, ssm_ratio=ssm_ratio, dt_rank=ssm_dt_rank,
                            act_layer=ssm_act_layer, d_conv=ssm_conv, conv_bias=ssm_conv_bias, dropout=ssm_drop_rate,
                            initialize=ssm_init, forward_type=forward_type, channel_first=channel_first)
         if self.mlp_branch:
-            self.norm2 = norm_layer(hidden_dim)
+            self.norm2 = LayerNorm(hidden_dim, for_matmul=True)
             self.mlp = Mlp(hidden_dim, int(hidden_dim * mlp_ratio), act_layer=mlp_act_layer, drop=mlp_drop_rate)
 
     def forward(self, x):  # drop_path is the identity in eval mode (inference tier)
@@ -246,7 +263,7 @@ class VSSM(nn.Module):
         self.dims = list(dims)
         acts = dict(silu=nn.SiLU, gelu=nn.GELU, relu=nn.ReLU, sigmoid=nn.Sigmoid)
         ssm_act, mlp_act = acts[ssm_act_layer.lower()], acts[mlp_act_layer.lower()]
-        LN = nn.LayerNorm
+        LN = LayerNorm
         if patchembed_version == "v1":
             self.patch_embed = nn.Sequential(
                 nn.Conv2d(in_chans, dims[0], kernel_size=patch_size, stride=patch_size, bias=True), Permute(0, 2, 3, 1),

@@ -119,35 +119,41 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int& 
     return warp_sums[wid] + inc - v;
 }
 
+// higher priority = processed earlier by greedy NMS: larger score, ties -> lower flat index
+__device__ __forceinline__ bool nms_better(float t, int r, float s, int q) { return t > s || (t == s && r < q); }
+
 __global__ void __launch_bounds__(NMS_THREADS) box_nms_kernel(const NmsParams p) {
-    __shared__ int8_t off_dy[NMS_MAX_OFFS], off_dx[NMS_MAX_OFFS];
+    __shared__ int8_t off_dy[NMS_MAX_OFFS + 32], off_dx[NMS_MAX_OFFS + 32];
     __shared__ int n_offs_s, alive_s;
     __shared__ int scan_ws[33];
     __shared__ unsigned hist[256];
     __shared__ unsigned sel_prefix, sel_remaining;
-    const int b = blockIdx.x, tid = threadIdx.x;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const int H = p.H, W = p.W, HW = H * W;
     const float* prob = p.prob + (int64_t)b * HW;
     uint8_t* st = p.state + (int64_t)b * HW;
 
-    // suppression footprint: offsets whose boxes overlap with IoU > iou  (fp32 arithmetic as torchvision)
+    // suppression footprint: offsets whose boxes overlap with IoU > iou (fp32 arithmetic as torchvision), nearest
+    // first so that the cooperative scan below usually exits after its first 32 offsets
     if (tid == 0) {
         int n = 0;
         const int R = (int)ceilf(p.size) - 1;
         const float area2 = 2.0f * p.size * p.size;
-        for (int dy = -R; dy <= R; ++dy)
-            for (int dx = -R; dx <= R; ++dx) {
-                if (dy == 0 && dx == 0) continue;
-                const float iw = p.size - fabsf((float)dx), ih = p.size - fabsf((float)dy);
-                if (iw <= 0.0f || ih <= 0.0f) continue;
-                const float inter = iw * ih;
-                if ((double)(inter / (area2 - inter)) > (double)p.iou) { off_dy[n] = (int8_t)dy; off_dx[n] = (int8_t)dx; ++n; }
-            }
+        for (int ring = 1; ring <= R; ++ring)
+            for (int dy = -ring; dy <= ring; ++dy)
+                for (int dx = -ring; dx <= ring; ++dx) {
+                    if (max(abs(dy), abs(dx)) != ring) continue;
+                    const float iw = p.size - fabsf((float)dx), ih = p.size - fabsf((float)dy);
+                    if (iw <= 0.0f || ih <= 0.0f) continue;
+                    const float inter = iw * ih;
+                    if ((double)(inter / (area2 - inter)) > (double)p.iou) { off_dy[n] = (int8_t)dy; off_dx[n] = (int8_t)dx; ++n; }
+                }
         n_offs_s = n;
         alive_s = 0;
     }
     __syncthreads();
     const int n_offs = n_offs_s;
+    const int HWr = (HW + 31) & ~31;          // warp-uniform loop bound for the ballot-based phases
 
     int local_alive = 0;
     for (int q = tid; q < HW; q += NMS_THREADS) {
@@ -163,38 +169,70 @@ __global__ void __launch_bounds__(NMS_THREADS) box_nms_kernel(const NmsParams p)
         __syncthreads();
         if (alive == 0) break;
         if (tid == 0) alive_s = 0;
-        // phase A: an undecided candidate with no undecided higher-priority candidate in its footprint is kept (NEW).
-        // Early exit on the first better neighbour: O(1) expected work for the non-maxima of a dense map.
-        for (int q = tid; q < HW; q += NMS_THREADS) {
-            if (st[q] != ST_ALIVE) continue;
-            const float s = prob[q];
-            const int y = q / W, x = q - y * W;
-            bool best = true;
-            for (int o = 0; o < n_offs; ++o) {
-                const int yy = y + off_dy[o], xx = x + off_dx[o];
-                if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-                const int r = yy * W + xx;
-                const uint8_t sr = st[r];
-                if (sr == ST_ALIVE || sr == ST_NEW) {   // NEW this round was ALIVE at round start
-                    const float t = prob[r];
-                    if (t > s || (t == s && r < q)) { best = false; break; }
+        // ---- phase A: an undecided candidate with no undecided higher-priority candidate in its footprint is kept.
+        //  A1 (lane per pixel): cheap necessary test on the 8-neighbourhood (always inside the footprint for s >= 2);
+        //  A2 (warp per surviving pixel): the 32 lanes test 32 footprint offsets at a time, exit on the first hit.
+        for (int q0 = tid - lane; q0 < HWr; q0 += NMS_THREADS) {
+            const int q = q0 + lane;
+            bool pre = false;
+            float s = 0.0f;
+            int y = 0, x = 0;
+            if (q < HW && st[q] == ST_ALIVE) {
+                s = prob[q];
+                y = q / W; x = q - y * W;
+                pre = true;
+                const int nn = n_offs < 8 ? n_offs : 8;
+                for (int o = 0; o < nn; ++o) {           // ring 1 comes first in the offset list
+                    const int yy = y + off_dy[o], xx = x + off_dx[o];
+                    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+                    const int r = yy * W + xx;
+                    const uint8_t sr = st[r];
+                    if ((sr == ST_ALIVE || sr == ST_NEW) && nms_better(prob[r], r, s, q)) pre = false;
                 }
             }
-            if (best) st[q] = ST_NEW;
+            unsigned todo = __ballot_sync(0xffffffffu, pre);
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int cq = q0 + src;
+                const float cs = __shfl_sync(0xffffffffu, s, src);
+                const int cy = __shfl_sync(0xffffffffu, y, src), cx = __shfl_sync(0xffffffffu, x, src);
+                bool beaten = false;
+                for (int o0 = 8; o0 < n_offs && !beaten; o0 += 32) {
+                    const int o = o0 + lane;
+                    bool hit = false;
+                    if (o < n_offs) {
+                        const int yy = cy + off_dy[o], xx = cx + off_dx[o];
+                        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+                            const int r = yy * W + xx;
+                            const uint8_t sr = st[r];
+                            hit = (sr == ST_ALIVE || sr == ST_NEW) && nms_better(prob[r], r, cs, cq);
+                        }
+                    }
+                    beaten = __any_sync(0xffffffffu, hit);
+                }
+                if (!beaten && lane == src) st[cq] = ST_NEW;   // NEW is treated like ALIVE by concurrent readers
+            }
         }
         __syncthreads();
-        // phase B (scatter): every NEW pixel suppresses the undecided candidates in its footprint and becomes KEPT.
-        // Two NEW pixels are never inside each other's footprint, so NEW is never overwritten.
-        for (int q = tid; q < HW; q += NMS_THREADS) {
-            if (st[q] != ST_NEW) continue;
-            const int y = q / W, x = q - y * W;
-            for (int o = 0; o < n_offs; ++o) {
-                const int yy = y + off_dy[o], xx = x + off_dx[o];
-                if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-                const int r = yy * W + xx;
-                if (st[r] == ST_ALIVE) st[r] = ST_NONE;
+        // ---- phase B (cooperative scatter): every NEW pixel suppresses the undecided candidates in its footprint and
+        // becomes KEPT.  Two NEW pixels are never inside each other's footprint, so NEW is never overwritten.
+        for (int q0 = tid - lane; q0 < HWr; q0 += NMS_THREADS) {
+            const int q = q0 + lane;
+            const bool isnew = q < HW && st[q] == ST_NEW;
+            unsigned todo = __ballot_sync(0xffffffffu, isnew);
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int cq = q0 + src, cy = cq / W, cx = cq - cy * W;
+                for (int o = lane; o < n_offs; o += 32) {
+                    const int yy = cy + off_dy[o], xx = cx + off_dx[o];
+                    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+                    const int r = yy * W + xx;
+                    if (st[r] == ST_ALIVE) st[r] = ST_NONE;
+                }
             }
-            st[q] = ST_KEPT;
+            if (isnew) st[q] = ST_KEPT;
         }
         __syncthreads();
         int still = 0;
@@ -240,41 +278,59 @@ __global__ void __launch_bounds__(NMS_THREADS) box_nms_kernel(const NmsParams p)
         }
     }
 
-    // ---- dense output + raster-order compaction: every thread owns a contiguous pixel range, one block scan
-    //      per quantity gives its output offset, so the order is the raster order ----
+    // ---- selection + raster-order compaction.  Warp w owns the contiguous pixel range [w*span, (w+1)*span): lanes
+    //      stride inside it (coalesced), ranks come from ballots, one block scan per quantity orders the warps. ----
     float* out = p.out ? p.out + (int64_t)b * HW : nullptr;
     int32_t* kp = p.kp ? p.kp + (int64_t)b * p.kp_cap * 2 : nullptr;
-    const int chunk = (HW + NMS_THREADS - 1) / NMS_THREADS;
-    const int q0 = min(tid * chunk, HW), q1 = min(q0 + chunk, HW);
-    int eq_before = 0;
+    const int wid = tid >> 5;
+    const int span = (((HW + 31) / 32 + 31) / 32) * 32;          // pixels per warp, multiple of 32
+    const int w0 = min(wid * span, HW), w1 = min(w0 + span, HW);
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int eq_base = 0;
     if (need_eq >= 0) {
-        int eq_local = 0;
-        for (int q = q0; q < q1; ++q) eq_local += (st[q] == ST_KEPT && __float_as_uint(prob[q]) == thr_bits);
+        int eq_warp = 0;
+        for (int q0 = w0; q0 < w1; q0 += 32) {
+            const int q = q0 + lane;
+            const bool eq = q < w1 && st[q] == ST_KEPT && __float_as_uint(prob[q]) == thr_bits;
+            eq_warp += __popc(__ballot_sync(0xffffffffu, eq));
+        }
         int tot;
-        eq_before = block_exclusive_scan(eq_local, scan_ws, tot);
+        const int ex = block_exclusive_scan(lane == 0 ? eq_warp : 0, scan_ws, tot);
+        eq_base = __shfl_sync(0xffffffffu, ex, 0);
     }
-    // pass 1: decide + count keypoints in my range (state byte: KEPT -> KEPT if selected else NONE)
-    int kp_local = 0;
-    for (int q = q0; q < q1; ++q) {
-        bool kept = false;
+    int kp_warp = 0;
+    for (int q0 = w0; q0 < w1; q0 += 32) {
+        const int q = q0 + lane;
+        bool kept = false, eq = false;
         float s = 0.0f;
-        if (st[q] == ST_KEPT) {
+        if (q < w1 && st[q] == ST_KEPT) {
             s = prob[q];
             const unsigned bits = __float_as_uint(s);
             if (need_eq < 0 || bits > thr_bits) kept = true;
-            else if (bits == thr_bits) { kept = eq_before < need_eq; ++eq_before; }
+            else if (bits == thr_bits) eq = true;
         }
-        st[q] = kept ? ST_KEPT : ST_NONE;
-        kp_local += kept && s > p.kp_thr;
+        if (need_eq >= 0) {
+            const unsigned em = __ballot_sync(0xffffffffu, eq);
+            if (eq && eq_base + __popc(em & lt_mask) < need_eq) kept = true;
+            eq_base += __popc(em);
+        }
+        if (q < w1) st[q] = kept ? ST_KEPT : ST_NONE;
+        kp_warp += __popc(__ballot_sync(0xffffffffu, kept && s > p.kp_thr));
     }
     int kp_total = 0, kp_off = 0;
-    if (kp || p.kp_count) kp_off = block_exclusive_scan(kp_local, scan_ws, kp_total);
+    if (kp || p.kp_count) {
+        const int ex = block_exclusive_scan(lane == 0 ? kp_warp : 0, scan_ws, kp_total);
+        kp_off = __shfl_sync(0xffffffffu, ex, 0);
+    }
     if (kp) {
-        for (int q = q0; q < q1; ++q)
-            if (st[q] == ST_KEPT && prob[q] > p.kp_thr) {
-                if (kp_off < p.kp_cap) { kp[2 * kp_off] = q / W; kp[2 * kp_off + 1] = q % W; }
-                ++kp_off;
-            }
+        for (int q0 = w0; q0 < w1; q0 += 32) {
+            const int q = q0 + lane;
+            const bool iskp = q < w1 && st[q] == ST_KEPT && prob[q] > p.kp_thr;
+            const unsigned m = __ballot_sync(0xffffffffu, iskp);
+            const int pos = kp_off + __popc(m & lt_mask);
+            if (iskp && pos < p.kp_cap) { kp[2 * pos] = q / W; kp[2 * pos + 1] = q % W; }
+            kp_off += __popc(m);
+        }
     }
     if (p.kp_count && tid == 0) p.kp_count[b] = kp_total;
     __syncthreads();

@@ -178,9 +178,11 @@ class SS2D(nn.Module):
         B, D, H, W = x.shape
         K, N, R, L = self.k_group, self.d_state, self.dt_rank, H * W
         xs = cross_scan_fn(x, True, True, False, 0)                                        # (B, 4, D, L)
-        x_dbl = F.conv1d(xs.view(B, -1, L), self.x_proj_weight.view(-1, D, 1), bias=None, groups=K)
-        dts, Bs, Cs = torch.split(x_dbl.view(B, K, -1, L), [R, N, N], dim=2)
-        dts = F.conv1d(dts.contiguous().view(B, -1, L), self.dt_projs_weight.view(K * D, -1, 1), groups=K)
+        # (K, R+2N, D) @ (B, K, D, L): strided-batched GEMMs straight on the scan layout (cuBLAS); the grouped
+        # conv1d of the reference's no_einsum path routes through cuDNN layout conversions that cost more than the math
+        x_dbl = torch.matmul(self.x_proj_weight.unsqueeze(0), xs)                          # (B, K, R+2N, L)
+        dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
+        dts = torch.matmul(self.dt_projs_weight.unsqueeze(0), dts).view(B, -1, L)          # (B, K*D, L)
         us = xs.view(B, -1, L)
         if dts.dtype != us.dtype:
             dts = dts.to(us.dtype)

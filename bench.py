@@ -216,12 +216,10 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    from xpoint_b200.sharding import max_over_ranks as _max
+
     def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return _max(ms, dev)
 
     # ---- warm-up -------------------------------------------------------------------------------------
     for _ in range(max(args.warmup, 3)):

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define XP_ABI_VERSION 1
+#define XP_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define XP_API __attribute__((visibility("default")))
@@ -62,6 +62,15 @@ XP_API int xp_check_device(void);
  * u/delta/B/C/z share in_dtype; out has out_dtype (XP_F32, or == in_dtype).  All strides are in
  * ELEMENTS; the seqlen stride of every tensor must be 1 (same rule as selective_scan_oflex.cpp:170-176).
  * dstate <= 256.  State and accumulation are always fp32.
+ *
+ * Fused CrossScan addressing (ABI 2; the three trailing fields, zero-initialised = the contract above):
+ * with u_group_div > 0 the u row of (batch b, group g, row dg inside the group) is
+ *     u + b*u_batch_stride + (g / u_group_div)*u_group_stride + dg*u_dim_stride ,
+ * so several scan directions read ONE copy of the activations (CrossScan without the 4x copy:
+ * csm_triton.py:22-29 routes l0 / l1 / L-1-l0 / L-1-l1 -- directions 0|2 share x, 1|3 share x^T).
+ * Bit g of reverse_group_mask makes group g (g < 64) walk the sequence backwards through memory: every
+ * per-token tensor of that group (u, delta, B, C, z) is read at token L-1-l at scan step l and out is written
+ * there, i.e. its y stays in natural (unflipped) memory order (CrossMerge's flips, csm_triton.py:56-62).
  */
 typedef struct {
     const void* u;
@@ -85,6 +94,10 @@ typedef struct {
     int32_t out_dtype;       /* xp_dtype */
     int32_t delta_softplus;  /* bool */
     int32_t force_generic;   /* debug/testing: 1 = always take the shape-generic kernel */
+    /* fused CrossScan addressing, see above (all zero = the plain selective_scan_fn contract) */
+    int64_t u_group_stride;       /* elements */
+    int64_t u_group_div;          /* 0 = classic addressing */
+    uint64_t reverse_group_mask;  /* bit g = group g runs backwards through memory */
 } xp_scan_args;
 
 XP_API int xp_selective_scan_fwd(const xp_scan_args* args, xp_stream_t stream);

@@ -122,6 +122,47 @@ def test_generic_kernel_matches_fast_kernel(N, KD, K, L):
     assert_close(lg.cpu().numpy(), rl, FP32_REL, "generic last")
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("N,L", [(1, 320), (1, 1280), (1, 2056), (1, 5120), (2, 776), (4, 264), (1, 24)])
+@pytest.mark.parametrize("use_z", [False, True])
+def test_fused_cross_scan_addressing(dtype, N, L, use_z):
+    """xp_scan_args.u_group_div / reverse_group_mask (ABI 2): directions that share one copy of the activations and
+    walk memory backwards (CrossScan / CrossMerge without copies, csm_triton.py:22-29,56-62).  The oracle sees the
+    materialised equivalent: u repeated per group, reversed groups flipped along L and flipped back."""
+    X, O = _imports()
+    from xpoint_b200.selective_scan import scan_forward
+    Bt, K, Dg, div, mask = 2, 4, 24, 2, 0b1010
+    u, dl, A, B, C, D, z, bias = make_inputs(L + 3 * N, Bt, K * Dg, K, N, L, dtype=dtype)
+    usrc = u[:, : (K // div) * Dg].contiguous()
+    ufull = torch.cat([usrc[:, (g // div) * Dg:(g // div + 1) * Dg] for g in range(K)], dim=1)
+    rev = [bool((mask >> g) & 1) for g in range(K)]
+
+    def flip_rows(t):      # (Bt, K*Dg, L)
+        t = t.clone().view(Bt, K, Dg, L)
+        for g in range(K):
+            if rev[g]:
+                t[:, g] = t[:, g].flip(-1)
+        return t.view(Bt, K * Dg, L)
+
+    def flip_groups(t):    # (Bt, K, N, L)
+        t = t.clone()
+        for g in range(K):
+            if rev[g]:
+                t[:, g] = t[:, g].flip(-1)
+        return t
+
+    zz = z if use_z else None
+    ref, rlast = O.selective_scan(flip_rows(ufull), flip_rows(dl), A, flip_groups(B), flip_groups(C), D,
+                                  None if zz is None else flip_rows(zz), bias, True, return_last_state=True)
+    ref = flip_rows(torch.from_numpy(np.ascontiguousarray(ref))).numpy()
+    tol = FP32_REL if dtype == torch.float32 else B16_REL
+    for force_generic in (False, True):
+        out, last = scan_forward(*cu(usrc, dl, A, B, C, D, zz, bias), True, True, True, force_generic=force_generic,
+                                 u_group_div=div, reverse_group_mask=mask)
+        assert_close(out.cpu().numpy(), ref, tol, f"fused addressing {dtype} N={N} L={L} generic={force_generic}")
+        assert_close(last.cpu().numpy(), rlast, tol, "fused addressing last state")
+
+
 def test_delta_groups_and_strided_views():
     X, O = _imports()
     u, dl, A, B, C, D, z, bias = make_inputs(5, 2, 24, 2, 4, 96, KD1=6)

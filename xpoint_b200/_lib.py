@@ -31,6 +31,7 @@ class ScanArgs(Structure):
                                   "C_batch_stride", "C_group_stride", "C_state_stride",
                                   "z_batch_stride", "z_dim_stride", "out_batch_stride", "out_dim_stride")]
         + [(n, c_int32) for n in ("in_dtype", "out_dtype", "delta_softplus", "force_generic")]
+        + [("u_group_stride", c_int64), ("u_group_div", c_int64), ("reverse_group_mask", ctypes.c_uint64)]
     )
 
 
@@ -88,7 +89,7 @@ def lib() -> ctypes.CDLL:
             fn = getattr(handle, name)  # raises AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if handle.xp_abi_version() != 1:
+        if handle.xp_abi_version() != 2:
             raise RuntimeError("libxpoint_b200.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -20,6 +20,10 @@
 //      warp per row, lanes along the sequence, one state at a time, scalar loads.
 //
 // All three keep fp32 state and accumulation (reference: csms6s.py:52-68).
+#include <stdlib.h>
+
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace xp {
@@ -29,6 +33,8 @@ struct ScanParams {
     const float* D; const void* z; const float* bias; void* out; float* last;
     int64_t batch, dim, delta_dim, groups, dstate, L;
     int64_t u_bs, u_ds, dl_bs, dl_ds, B_bs, B_gs, B_ss, C_bs, C_gs, C_ss, z_bs, z_ds, o_bs, o_ds;
+    int64_t u_gs, u_gdiv;   // u row of (b, g, dg) = u + b*u_bs + (g / u_gdiv)*u_gs + dg*u_ds
+    uint64_t rev_mask;      // bit g: group g walks memory backwards (all tensors, including out)
     int softplus;
     int rows_per_warp;   // scan_lanes only
 };
@@ -54,7 +60,9 @@ __global__ void __launch_bounds__(GEN_WARPS * 32) scan_generic_kernel(const Scan
     const int64_t g = d / (p.dim / p.groups);
     const int64_t dd = d / (p.dim / p.delta_dim);
     const int N = (int)p.dstate;
-    const IN_T* u = (const IN_T*)p.u + b * p.u_bs + d * p.u_ds;
+    const int64_t Dg = p.dim / p.groups;
+    const bool rev = g < 64 && ((p.rev_mask >> g) & 1);
+    const IN_T* u = (const IN_T*)p.u + b * p.u_bs + (g / p.u_gdiv) * p.u_gs + (d - g * Dg) * p.u_ds;
     const IN_T* dl = (const IN_T*)p.delta + b * p.dl_bs + dd * p.dl_ds;
     const IN_T* Bm = (const IN_T*)p.Bm + b * p.B_bs + g * p.B_gs;
     const IN_T* Cm = (const IN_T*)p.Cm + b * p.C_bs + g * p.C_gs;
@@ -70,11 +78,12 @@ __global__ void __launch_bounds__(GEN_WARPS * 32) scan_generic_kernel(const Scan
     for (int64_t t0 = 0; t0 < p.L; t0 += 32 * GEN_C) {
         float uv[GEN_C], dv[GEN_C], y[GEN_C];
         const int64_t l0 = t0 + lane * GEN_C;
+        auto mem = [&](int64_t l) { return rev ? p.L - 1 - l : l; };   // scan position -> memory token
 #pragma unroll
         for (int j = 0; j < GEN_C; ++j) {
             const bool ok = l0 + j < p.L;
-            uv[j] = ok ? to_f32(u[l0 + j]) : 0.0f;
-            dv[j] = ok ? delta_act(to_f32(dl[l0 + j]), bias, p.softplus) : 0.0f;  // 0 -> identity step
+            uv[j] = ok ? to_f32(u[mem(l0 + j)]) : 0.0f;
+            dv[j] = ok ? delta_act(to_f32(dl[mem(l0 + j)]), bias, p.softplus) : 0.0f;  // 0 -> identity step
             y[j] = Dv * uv[j];
         }
         for (int n = 0; n < N; ++n) {
@@ -85,7 +94,7 @@ __global__ void __launch_bounds__(GEN_WARPS * 32) scan_generic_kernel(const Scan
             for (int j = 0; j < GEN_C; ++j) {
                 const bool ok = l0 + j < p.L;
                 const float a = __expf(dv[j] * An);
-                const float bu = ok ? (dv[j] * to_f32(Bm[n * p.B_ss + l0 + j])) * uv[j] : 0.0f;
+                const float bu = ok ? (dv[j] * to_f32(Bm[n * p.B_ss + mem(l0 + j)])) * uv[j] : 0.0f;
                 S = fmaf(a, S, bu);
                 P *= a;
                 hl[j] = S; pl[j] = P;
@@ -103,7 +112,7 @@ __global__ void __launch_bounds__(GEN_WARPS * 32) scan_generic_kernel(const Scan
             for (int j = 0; j < GEN_C; ++j) {
                 const bool ok = l0 + j < p.L;
                 const float h = fmaf(pl[j], hin, hl[j]);
-                if (ok) y[j] = fmaf(h, to_f32(Cm[n * p.C_ss + l0 + j]), y[j]);
+                if (ok) y[j] = fmaf(h, to_f32(Cm[n * p.C_ss + mem(l0 + j)]), y[j]);
             }
             __syncwarp();
             if (lane == 31) carry[n] = fmaf(P, hc, S);
@@ -113,8 +122,8 @@ __global__ void __launch_bounds__(GEN_WARPS * 32) scan_generic_kernel(const Scan
         for (int j = 0; j < GEN_C; ++j)
             if (l0 + j < p.L) {
                 float v = y[j];
-                if (z) v *= silu_f(to_f32(z[l0 + j]));
-                out[l0 + j] = from_f32<OUT_T>(v);
+                if (z) v *= silu_f(to_f32(z[mem(l0 + j)]));
+                out[mem(l0 + j)] = from_f32<OUT_T>(v);
             }
     }
     if (p.last)
@@ -124,200 +133,329 @@ __global__ void __launch_bounds__(GEN_WARPS * 32) scan_generic_kernel(const Scan
 // ============================================================================================
 // lanes kernel (dstate 1 | 2)
 // ============================================================================================
-// Per-warp software pipeline, no CTA-wide synchronisation:
-//   * lane 0 streams the next LN_STAGES (row, step) items with 1-D bulk async copies (cp.async.bulk -> UBLKCP,
-//     the TMA engine) into a per-warp shared-memory ring; completion is tracked by mbarriers, so the loads cost
-//     no registers and no scoreboard slots (a register prefetch aliased a scoreboard slot with the first SHFL of
-//     the next iteration and serialised the pipeline -- profiles/r1_scan_n1_v1.md);
-//   * every item is 256 consecutive tokens of one channel row (1 KiB fp32 per tensor): long DRAM bursts;
-//   * B/C chunks are loaded once per step into a double buffer and reused by the RW rows of the warp;
-//   * lanes read 8 tokens each (2 x LDS.128, conflict-free), scan them in registers, and the 32 lane chunks are
-//     combined with a warp-shuffle prefix scan of the affine maps h -> P*h + S; y leaves through 128-bit stores.
-constexpr int LN_WARPS = 4;
-constexpr int LN_C = 8;        // tokens per lane per step -> 256-token steps
-constexpr int LN_STAGES = 4;   // ring depth (items in flight per warp)
+// CTA = LN_CONSUMERS consumer warps + 1 producer warp; every consumer warp runs a private pipeline over its own
+// (row, step) items, there is no CTA-wide synchronisation after start-up.
+//   * producer warp: lane w feeds consumer warp w.  Per item it waits (non-blocking poll) for the ring slot's
+//     "empty" mbarrier and streams u/delta[/z] of one channel row and TOK = 32*C consecutive tokens with 1-D bulk
+//     async copies (cp.async.bulk -> UBLKCP, the TMA engine) into the consumer's shared-memory ring; B/C chunks go
+//     into a separate double buffer once per step and are shared by the RW rows of the warp.  The consumers spend
+//     no issue slots on address arithmetic and no registers / scoreboard slots on loads in flight.
+//   * consumer warp: lanes read C tokens each (LDS.128), scan them sequentially in registers, and the 32 lane
+//     chunks are combined with a warp-shuffle prefix scan of the affine maps h -> P*h + S; y leaves through
+//     128-bit stores.  Per-row constants and the running state live in a small per-warp shared-memory table.
+//   * full steps (all 32*C tokens valid) run a predicate-free body; only the last step of a row is masked.
+//   * reversed groups (xp_scan_args.reverse_group_mask) walk memory backwards: the producer fetches the mirrored
+//     window, lanes take mirrored chunks and reverse the element order in registers -- no extra instructions.
+//   * 16-bit inputs use softplus(x) = ln2 * lg2(1 + 2^(x*log2e)) with ln2 / log2e folded into A, bias and B
+//     (4 FP32 + 2 MUFU per token instead of ~14 instructions); its error (~2e-7 absolute on delta') is far
+//     below the 16-bit input quantisation.  fp32 inputs keep the series-corrected softplus_f.
+constexpr int LN_STAGES = 4;     // u/delta ring depth per consumer warp
+constexpr int LN_BCS = 2;        // B/C buffer depth per consumer warp
+constexpr int LN_MAXROWS = 8;    // max channel rows per warp
 
-template <typename IN_T> __device__ __forceinline__ void lds_tokens8(const uint8_t* p, float (&f)[LN_C]);
-template <> __device__ __forceinline__ void lds_tokens8<float>(const uint8_t* p, float (&f)[LN_C]) {
-    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 16);
-    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+template <typename IN_T> __device__ __forceinline__ void widen16(const uint4& v, float (&f)[16 / sizeof(IN_T)]);
+template <> __device__ __forceinline__ void widen16<float>(const uint4& v, float (&f)[4]) {
+    f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y); f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
 }
-template <> __device__ __forceinline__ void lds_tokens8<__half>(const uint8_t* p, float (&f)[LN_C]) {
-    VecIO<__half, 8>::widen(*reinterpret_cast<const uint4*>(p), f);
-}
-template <> __device__ __forceinline__ void lds_tokens8<__nv_bfloat16>(const uint8_t* p, float (&f)[LN_C]) {
-    VecIO<__nv_bfloat16, 8>::widen(*reinterpret_cast<const uint4*>(p), f);
+template <> __device__ __forceinline__ void widen16<__half>(const uint4& v, float (&f)[8]) { VecIO<__half, 8>::widen(v, f); }
+template <> __device__ __forceinline__ void widen16<__nv_bfloat16>(const uint4& v, float (&f)[8]) {
+    VecIO<__nv_bfloat16, 8>::widen(v, f);
 }
 
-template <typename OUT_T> __device__ __forceinline__ void store_vec8(OUT_T* p, const float (&y)[LN_C]);
-template <> __device__ __forceinline__ void store_vec8<float>(float* p, const float (&y)[LN_C]) {
-    const float a[4] = {y[0], y[1], y[2], y[3]}, b[4] = {y[4], y[5], y[6], y[7]};
+// C consecutive elements from shared memory, widened to fp32; REV hands them back in reversed order
+template <typename IN_T, int C, bool REV> __device__ __forceinline__ void lds_tokens(uint32_t saddr, float (&f)[C]) {
+    constexpr int PER = 16 / (int)sizeof(IN_T);
+    static_assert(C % PER == 0, "lane chunk must be whole 16-byte vectors");
+#pragma unroll
+    for (int v = 0; v < C / PER; ++v) {
+        float w[PER];
+        widen16<IN_T>(lds128(saddr + 16 * v), w);
+#pragma unroll
+        for (int i = 0; i < PER; ++i) f[REV ? C - 1 - (v * PER + i) : v * PER + i] = w[i];
+    }
+}
+
+template <typename OUT_T> __device__ __forceinline__ void stg16(OUT_T* p, const float* v);   // one 16-byte store
+template <> __device__ __forceinline__ void stg16<float>(float* p, const float* v) {
+    const float a[4] = {v[0], v[1], v[2], v[3]};
     VecIO<float, 4>::store(p, a);
-    VecIO<float, 4>::store(p + 4, b);
 }
-template <> __device__ __forceinline__ void store_vec8<__half>(__half* p, const float (&y)[LN_C]) { VecIO<__half, 8>::store(p, y); }
-template <> __device__ __forceinline__ void store_vec8<__nv_bfloat16>(__nv_bfloat16* p, const float (&y)[LN_C]) {
-    VecIO<__nv_bfloat16, 8>::store(p, y);
+template <> __device__ __forceinline__ void stg16<__half>(__half* p, const float* v) {
+    const float a[8] = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]};
+    VecIO<__half, 8>::store(p, a);
+}
+template <> __device__ __forceinline__ void stg16<__nv_bfloat16>(__nv_bfloat16* p, const float* v) {
+    const float a[8] = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]};
+    VecIO<__nv_bfloat16, 8>::store(p, a);
 }
 
-template <int NST, typename IN_T, bool HAS_Z> struct LanesCfg {
-    static constexpr int CHUNK = 32 * LN_C * (int)sizeof(IN_T);        // bytes of one 256-token chunk
-    static constexpr int ITEM = CHUNK * (HAS_Z ? 3 : 2);                // u, delta [, z]
-    static constexpr int BC = 2 * NST * CHUNK;                          // B rows then C rows
-    static constexpr int WARP_BYTES = LN_STAGES * ITEM + 2 * BC;
-    static constexpr int NBARS = LN_STAGES + 2;
-    static constexpr int SMEM = LN_WARPS * (WARP_BYTES + NBARS * 8) + 16;
+// y[0..C) in scan order -> C consecutive memory elements starting at gp (reversed when REV).  nv = number of valid
+// scan-order tokens of this lane (C in full steps); vectors are all-or-nothing (host guarantees L % vector == 0).
+template <typename OUT_T, int C, bool REV, bool FULL>
+__device__ __forceinline__ void store_tokens(OUT_T* gp, const float (&y)[C], int nv) {
+    constexpr int PER = 16 / (int)sizeof(OUT_T);
+    float m[C];
+#pragma unroll
+    for (int j = 0; j < C; ++j) m[REV ? C - 1 - j : j] = y[j];
+#pragma unroll
+    for (int v = 0; v < C / PER; ++v) {
+        const int jmin = REV ? C - (v + 1) * PER : v * PER;   // lowest scan index inside memory vector v
+        if (FULL || jmin < nv) stg16<OUT_T>(gp + v * PER, &m[v * PER]);
+    }
+}
+
+template <int NST, typename IN_T, int C, bool HAS_Z, int NW> struct LanesCfg {
+    static constexpr int TOK = 32 * C;                                   // tokens per step
+    static constexpr int CHUNK = TOK * (int)sizeof(IN_T);                // bytes of one row chunk
+    static constexpr int ITEM = CHUNK * (HAS_Z ? 3 : 2);                 // u, delta [, z]
+    static constexpr int BC = 2 * NST * CHUNK;                           // B rows then C rows
+    static constexpr int RCF = NST == 1 ? 4 : 8;                         // floats of per-row constants
+    static constexpr int RC_BYTES = LN_MAXROWS * RCF * 4;
+    static constexpr int WARP_BYTES = LN_STAGES * ITEM + LN_BCS * BC + RC_BYTES;
+    static constexpr int NBARS = 2 * LN_STAGES + 2 * LN_BCS;             // full/empty + bcfull/bcempty
+    static constexpr int SMEM = NW * (WARP_BYTES + NBARS * 8) + 16;
 };
 
-template <int NST, typename IN_T, typename OUT_T, bool HAS_Z>
-__global__ void __launch_bounds__(LN_WARPS * 32) scan_lanes_kernel(const ScanParams p) {
-    using Cfg = LanesCfg<NST, IN_T, HAS_Z>;
-    constexpr int TOK = 32 * LN_C;
-    extern __shared__ uint8_t smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 15) & ~uintptr_t(15));
-    uint8_t* ring = base + warp * Cfg::WARP_BYTES;
-    uint8_t* bcbuf = ring + LN_STAGES * Cfg::ITEM;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(base + LN_WARPS * Cfg::WARP_BYTES) + warp * Cfg::NBARS;
-    uint64_t* bcbars = bars + LN_STAGES;
-
-    const int64_t wid = (int64_t)blockIdx.x * LN_WARPS + warp;
+struct LanesWarp {   // decoded work assignment of one consumer warp
+    int64_t b, g, d0;
+    int nrows;
+    bool valid;
+};
+__device__ __forceinline__ LanesWarp lanes_decode(const ScanParams& p, int64_t wid) {
+    LanesWarp w;
     const int RW = p.rows_per_warp;
     const int64_t Dg = p.dim / p.groups;
-    const int64_t rb_per_group = (Dg + RW - 1) / RW;
-    if (wid >= p.batch * p.groups * rb_per_group) return;
-    const int64_t rb = wid % rb_per_group;
-    const int64_t g = (wid / rb_per_group) % p.groups;
-    const int64_t b = wid / (rb_per_group * p.groups);
-    const int64_t d0 = g * Dg + rb * RW;
-    const int nrows = (int)min((int64_t)RW, Dg - rb * RW);
-    const int S = min(LN_STAGES, nrows);     // ring depth actually used (keeps the B/C double buffer safe)
+    const int64_t rbpg = (Dg + RW - 1) / RW;
+    w.valid = wid < p.batch * p.groups * rbpg;
+    const int64_t rb = wid % rbpg;
+    w.g = (wid / rbpg) % p.groups;
+    w.b = wid / (rbpg * p.groups);
+    w.d0 = w.g * Dg + rb * RW;
+    w.nrows = w.valid ? (int)min((int64_t)RW, Dg - rb * RW) : 0;
+    return w;
+}
 
-    const IN_T* ub = (const IN_T*)p.u + b * p.u_bs + d0 * p.u_ds;
-    const IN_T* db = (const IN_T*)p.delta + b * p.dl_bs + d0 * p.dl_ds;
-    const IN_T* zb = HAS_Z ? (const IN_T*)p.z + b * p.z_bs + d0 * p.z_ds : nullptr;
-    const IN_T* Bb = (const IN_T*)p.Bm + b * p.B_bs + g * p.B_gs;
-    const IN_T* Cb = (const IN_T*)p.Cm + b * p.C_bs + g * p.C_gs;
-    OUT_T* ob = (OUT_T*)p.out + b * p.o_bs + d0 * p.o_ds + lane * LN_C;
-
-    // per-row constants live in lane r (r < nrows <= 32); broadcast with shuffles inside the row loop
-    float A2_l[NST], carry_l[NST], bias_l = 0.0f, D_l = 0.0f;
-#pragma unroll
-    for (int n = 0; n < NST; ++n) { A2_l[n] = 0.0f; carry_l[n] = 0.0f; }
-    if (lane < nrows) {
-#pragma unroll
-        for (int n = 0; n < NST; ++n) A2_l[n] = p.A[(d0 + lane) * NST + n] * kLog2e;
-        bias_l = p.bias ? p.bias[d0 + lane] : 0.0f;
-        D_l = p.D ? p.D[d0 + lane] : 0.0f;
-    }
-
+template <int NST, typename IN_T, int C, bool HAS_Z, int NW>
+__device__ __forceinline__ void lanes_producer(const ScanParams& p, uint8_t* base, int lane) {
+    using Cfg = LanesCfg<NST, IN_T, C, HAS_Z, NW>;
+    constexpr int TOK = Cfg::TOK;
+    constexpr int ES = (int)sizeof(IN_T);
+    const bool mine = lane < NW;
+    const LanesWarp w = lanes_decode(p, (int64_t)blockIdx.x * NW + (mine ? lane : 0));
+    uint8_t* ring = base + (mine ? lane : 0) * Cfg::WARP_BYTES;
+    uint8_t* bcbuf = ring + LN_STAGES * Cfg::ITEM;
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + NW * Cfg::WARP_BYTES) + (mine ? lane : 0) * Cfg::NBARS;
+    uint64_t* empty = full + LN_STAGES;
+    uint64_t* bcfull = empty + LN_STAGES;
+    uint64_t* bcempty = bcfull + LN_BCS;
+    const int64_t Dg = p.dim / p.groups;
+    const int64_t dg0 = w.d0 - w.g * Dg;
+    const bool rev = (p.rev_mask >> (w.g & 63)) & 1 && w.g < 64;
+    const IN_T* ub = (const IN_T*)p.u + w.b * p.u_bs + (w.g / p.u_gdiv) * p.u_gs + dg0 * p.u_ds;
+    const IN_T* db = (const IN_T*)p.delta + w.b * p.dl_bs + w.d0 * p.dl_ds;
+    const IN_T* zb = HAS_Z ? (const IN_T*)p.z + w.b * p.z_bs + w.d0 * p.z_ds : nullptr;
+    const IN_T* Bb = (const IN_T*)p.Bm + w.b * p.B_bs + w.g * p.B_gs;
+    const IN_T* Cb = (const IN_T*)p.Cm + w.b * p.C_bs + w.g * p.C_gs;
     const int nsteps = (int)((p.L + TOK - 1) / TOK);
-    const int total = nsteps * nrows;
-    // producer cursor (lane 0): next item to issue
-    int is = 0, ir = 0, islot = 0;
-    auto issue = [&]() {
-        const int64_t t0 = (int64_t)is * TOK;
-        const uint32_t bytes = (uint32_t)(min((int64_t)TOK, p.L - t0) * (int64_t)sizeof(IN_T));
-        uint8_t* dst = ring + islot * Cfg::ITEM;
-        mbar_arrive_expect_tx(&bars[islot], bytes * (HAS_Z ? 3 : 2));
-        bulk_load(dst, ub + ir * p.u_ds + t0, bytes, &bars[islot]);
-        bulk_load(dst + Cfg::CHUNK, db + ir * p.dl_ds + t0, bytes, &bars[islot]);
-        if (HAS_Z) bulk_load(dst + 2 * Cfg::CHUNK, zb + ir * p.z_ds + t0, bytes, &bars[islot]);
-        if (ir == 0) {
-            uint8_t* bc = bcbuf + (is & 1) * Cfg::BC;
-            mbar_arrive_expect_tx(&bcbars[is & 1], bytes * 2 * NST);
+    const int total = (mine && w.valid) ? nsteps * w.nrows : 0;
+    int it = 0, r = 0, step = 0, slot = 0;
+    uint32_t fill = 0;          // how many times the ring has wrapped
+    while (true) {
+        const bool active = it < total;
+        if (!__any_sync(0xffffffffu, active)) break;
+        bool issued = false;
+        if (active) {
+            bool ok = mbar_test_wait(&empty[slot], (fill - 1u) & 1u);          // fill 0: parity 1 passes on a fresh barrier
+            const int bs = step % LN_BCS;
+            if (ok && r == 0) ok = mbar_test_wait(&bcempty[bs], ((uint32_t)(step / LN_BCS) - 1u) & 1u);
+            if (ok) {
+                const int64_t t0 = (int64_t)step * TOK;
+                const int64_t valid = min((int64_t)TOK, p.L - t0);
+                const int64_t m0 = rev ? p.L - t0 - valid : t0;                 // first memory token of the window
+                const uint32_t off = rev ? (uint32_t)((TOK - valid) * ES) : 0u; // mirrored windows are right-aligned
+                const uint32_t bytes = (uint32_t)(valid * ES);
+                uint8_t* dst = ring + slot * Cfg::ITEM + off;
+                mbar_arrive_expect_tx(&full[slot], bytes * (HAS_Z ? 3 : 2));
+                bulk_load(dst, ub + r * p.u_ds + m0, bytes, &full[slot]);
+                bulk_load(dst + Cfg::CHUNK, db + r * p.dl_ds + m0, bytes, &full[slot]);
+                if (HAS_Z) bulk_load(dst + 2 * Cfg::CHUNK, zb + r * p.z_ds + m0, bytes, &full[slot]);
+                if (r == 0) {
+                    uint8_t* bc = bcbuf + bs * Cfg::BC + off;
+                    mbar_arrive_expect_tx(&bcfull[bs], bytes * 2 * NST);
 #pragma unroll
-            for (int n = 0; n < NST; ++n) {
-                bulk_load(bc + n * Cfg::CHUNK, Bb + n * p.B_ss + t0, bytes, &bcbars[is & 1]);
-                bulk_load(bc + (NST + n) * Cfg::CHUNK, Cb + n * p.C_ss + t0, bytes, &bcbars[is & 1]);
+                    for (int n = 0; n < NST; ++n) {
+                        bulk_load(bc + n * Cfg::CHUNK, Bb + n * p.B_ss + m0, bytes, &bcfull[bs]);
+                        bulk_load(bc + (NST + n) * Cfg::CHUNK, Cb + n * p.C_ss + m0, bytes, &bcfull[bs]);
+                    }
+                }
+                if (++r == w.nrows) { r = 0; ++step; }
+                if (++slot == LN_STAGES) { slot = 0; ++fill; }
+                ++it;
+                issued = true;
             }
         }
-        if (++ir == nrows) { ir = 0; ++is; }
-        if (++islot == S) islot = 0;
-    };
-    if (lane == 0) {
-        for (int s = 0; s < Cfg::NBARS; ++s) mbar_init(&bars[s], 1);
-        fence_mbar_init();
-        fence_proxy_async();
-        for (int s = 0; s < S && s < total; ++s) issue();
+        if (!__any_sync(0xffffffffu, issued)) __nanosleep(40);
+    }
+}
+
+template <int NST, typename IN_T, typename OUT_T, int C, bool HAS_Z, bool SOFTPLUS, bool REV, int NW>
+__device__ __forceinline__ void lanes_consumer(const ScanParams& p, uint8_t* base, const LanesWarp& w, int warp, int lane) {
+    using Cfg = LanesCfg<NST, IN_T, C, HAS_Z, NW>;
+    constexpr int TOK = Cfg::TOK, RCF = Cfg::RCF;
+    constexpr bool FAST = SOFTPLUS && sizeof(IN_T) == 2;
+    // everything below addresses shared memory through 32-bit shared-window addresses (LDS/STS, not generic LD/ST)
+    const uint32_t ring = smem_u32(base) + warp * Cfg::WARP_BYTES;
+    const uint32_t bcbuf = ring + LN_STAGES * Cfg::ITEM;
+    const uint32_t rcs = bcbuf + LN_BCS * Cfg::BC;
+    float* rc = reinterpret_cast<float*>(base + warp * Cfg::WARP_BYTES + LN_STAGES * Cfg::ITEM + LN_BCS * Cfg::BC);
+    const uint32_t full = smem_u32(base) + NW * Cfg::WARP_BYTES + warp * Cfg::NBARS * 8;
+    const uint32_t empty = full + LN_STAGES * 8;
+    const uint32_t bcfull = empty + LN_STAGES * 8;
+    const uint32_t bcempty = bcfull + LN_BCS * 8;
+
+    // per-row constants {A[n]*s, bias*s', D, carry[n]}  (s = log2e, s' = 1 unless FAST: s = 1, s' = log2e)
+    if (lane < w.nrows) {
+        float* k = rc + lane * RCF;
+#pragma unroll
+        for (int n = 0; n < NST; ++n) {
+            k[n] = p.A[(w.d0 + lane) * NST + n] * (FAST ? 1.0f : kLog2e);
+            k[NST + 2 + n] = 0.0f;
+        }
+        k[NST] = (p.bias ? p.bias[w.d0 + lane] : 0.0f) * (FAST ? kLog2e : 1.0f);
+        k[NST + 1] = p.D ? p.D[w.d0 + lane] : 0.0f;
     }
     __syncwarp();
 
-    float Bv[NST][LN_C], Cv[NST][LN_C];
+    const int ci = REV ? 31 - lane : lane;
+    const uint32_t lane_off = (uint32_t)(ci * C * (int)sizeof(IN_T));
+    OUT_T* orow0 = (OUT_T*)p.out + w.b * p.o_bs + w.d0 * p.o_ds;
+    const int nsteps = (int)((p.L + TOK - 1) / TOK);
+    const int total = nsteps * w.nrows;
+
+    float Bv[NST][C], Cv[NST][C];
     int r = 0, step = 0, slot = 0;
     uint32_t phase = 0;
     for (int it = 0; it < total; ++it) {
-        const int64_t l0 = (int64_t)step * TOK + lane * LN_C;
-        const bool ok = l0 < p.L;   // L % vector width == 0 is guaranteed by the host: lane chunks are all-or-nothing
+        const int64_t tok0 = (int64_t)step * TOK + lane * C;       // first scan-order token of this lane
+        const bool full_step = (int64_t)(step + 1) * TOK <= p.L;
+        const int nv = full_step ? C : (int)max((int64_t)0, min((int64_t)C, p.L - tok0));
         if (r == 0) {
-            mbar_wait(&bcbars[step & 1], (uint32_t)((step >> 1) & 1));
-            const uint8_t* bc = bcbuf + (step & 1) * Cfg::BC + lane * (LN_C * (int)sizeof(IN_T));
+            const int bs = step % LN_BCS;
+            mbar_wait_s(bcfull + bs * 8, (uint32_t)(step / LN_BCS) & 1u);
+            const uint32_t bc = bcbuf + bs * Cfg::BC + lane_off;
 #pragma unroll
             for (int n = 0; n < NST; ++n) {
-                lds_tokens8<IN_T>(bc + n * Cfg::CHUNK, Bv[n]);
-                lds_tokens8<IN_T>(bc + (NST + n) * Cfg::CHUNK, Cv[n]);
+                lds_tokens<IN_T, C, REV>(bc + n * Cfg::CHUNK, Bv[n]);
+                lds_tokens<IN_T, C, REV>(bc + (NST + n) * Cfg::CHUNK, Cv[n]);
+#pragma unroll
+                for (int j = 0; j < C; ++j) {
+                    if (FAST) Bv[n][j] *= kLn2;
+                    if (!full_step && j >= nv) { Bv[n][j] = 0.0f; Cv[n][j] = 0.0f; }   // stale smem may hold NaN/Inf
+                }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_s(bcempty + bs * 8);
         }
-        mbar_wait(&bars[slot], phase);
-        const uint8_t* item = ring + slot * Cfg::ITEM + lane * (LN_C * (int)sizeof(IN_T));
-        float uv[LN_C], dv[LN_C], zv[LN_C];
-        lds_tokens8<IN_T>(item, uv);
-        lds_tokens8<IN_T>(item + Cfg::CHUNK, dv);
-        if (HAS_Z) lds_tokens8<IN_T>(item + 2 * Cfg::CHUNK, zv);
-        __syncwarp();                                   // every lane has drained this slot
-        if (lane == 0 && it + S < total) issue();       // refill it with item it + S
-        if (++slot == S) { slot = 0; phase ^= 1; }
+        mbar_wait_s(full + slot * 8, phase);
+        const uint32_t item = ring + slot * Cfg::ITEM + lane_off;
+        float uv[C], dv[C], zv[HAS_Z ? C : 1];
+        lds_tokens<IN_T, C, REV>(item, uv);
+        lds_tokens<IN_T, C, REV>(item + Cfg::CHUNK, dv);
+        if constexpr (HAS_Z) lds_tokens<IN_T, C, REV>(item + 2 * Cfg::CHUNK, zv);
+        float kc[RCF];
+#pragma unroll
+        for (int q = 0; q < RCF / 4; ++q) {
+            const uint4 t = lds128(rcs + (r * RCF + 4 * q) * 4);
+            kc[4 * q] = __uint_as_float(t.x); kc[4 * q + 1] = __uint_as_float(t.y);
+            kc[4 * q + 2] = __uint_as_float(t.z); kc[4 * q + 3] = __uint_as_float(t.w);
+        }
+        __syncwarp();                                    // every lane has drained the slot (and read the row table)
+        if (lane == 0) mbar_arrive_s(empty + slot * 8);  // hand it back to the producer
+        if (++slot == LN_STAGES) { slot = 0; phase ^= 1u; }
 
-        const float bias = __shfl_sync(0xffffffffu, bias_l, r);
-        const float Dv = __shfl_sync(0xffffffffu, D_l, r);
-        float y[LN_C];
+        const float kb = kc[NST], kD = kc[NST + 1];
+        auto body = [&](auto full_tag) {
+            constexpr bool FULL = decltype(full_tag)::value;
+            float y[C], lw[C];
 #pragma unroll
-        for (int j = 0; j < LN_C; ++j) {
-            const float dl = delta_act(dv[j], bias, p.softplus);
-            dv[j] = ok ? dl : 0.0f;                     // 0 -> a = 1, b = 0: identity step past the end
-            y[j] = Dv * uv[j];
-            uv[j] = ok ? uv[j] * dl : 0.0f;             // delta * u
-        }
-#pragma unroll
-        for (int n = 0; n < NST; ++n) {
-            const float A2 = __shfl_sync(0xffffffffu, A2_l[n], r);
-            const float hc = __shfl_sync(0xffffffffu, carry_l[n], r);
-            float hl[LN_C], pl[LN_C];
-            float P = 1.0f, S_ = 0.0f;
-#pragma unroll
-            for (int j = 0; j < LN_C; ++j) {
-                const float a = ex2_approx(dv[j] * A2);
-                S_ = fmaf(a, S_, ok ? uv[j] * Bv[n][j] : 0.0f);
-                P *= a;
-                hl[j] = S_; pl[j] = P;
+            for (int j = 0; j < C; ++j) {
+                float l;
+                if constexpr (FAST) {                    // l = log2e * softplus(delta + bias)
+                    const float t = fmaf(dv[j], kLog2e, kb);
+                    l = fmaxf(lg2_approx(1.0f + ex2_approx(fminf(t, 100.0f))), t);
+                } else {
+                    const float d = dv[j] + kb;
+                    l = SOFTPLUS ? softplus_f(d) : d;
+                }
+                if (!FULL && j >= nv) { l = 0.0f; uv[j] = 0.0f; }   // identity step past the end
+                lw[j] = l;
+                y[j] = kD * uv[j];
+                uv[j] *= l;
             }
-            // warp-level inclusive scan of the affine maps h -> P*h + S across the 32 lane chunks
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const float Pp = __shfl_up_sync(0xffffffffu, P, o), Sp = __shfl_up_sync(0xffffffffu, S_, o);
-                if (lane >= o) { S_ = fmaf(P, Sp, S_); P *= Pp; }
+            for (int n = 0; n < NST; ++n) {
+                const float kA = kc[n], hc = kc[NST + 2 + n];
+                float hl[C], pl[C];
+                float P = 1.0f, S_ = 0.0f;
+#pragma unroll
+                for (int j = 0; j < C; ++j) {
+                    const float a = ex2_approx(lw[j] * kA);
+                    S_ = fmaf(a, S_, uv[j] * Bv[n][j]);
+                    P *= a;
+                    hl[j] = S_; pl[j] = P;
+                }
+                // warp-level inclusive scan of the affine maps h -> P*h + S across the 32 lane chunks
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const float Pp = __shfl_up_sync(0xffffffffu, P, o), Sp = __shfl_up_sync(0xffffffffu, S_, o);
+                    if (lane >= o) { S_ = fmaf(P, Sp, S_); P *= Pp; }
+                }
+                float Pe = __shfl_up_sync(0xffffffffu, P, 1), Se = __shfl_up_sync(0xffffffffu, S_, 1);
+                if (lane == 0) { Pe = 1.0f; Se = 0.0f; }
+                const float hin = fmaf(Pe, hc, Se);
+#pragma unroll
+                for (int j = 0; j < C; ++j) y[j] = fmaf(fmaf(pl[j], hin, hl[j]), Cv[n][j], y[j]);
+                if (lane == 31) sts32(rcs + (r * RCF + NST + 2 + n) * 4, fmaf(P, hc, S_));
             }
-            float Pe = __shfl_up_sync(0xffffffffu, P, 1), Se = __shfl_up_sync(0xffffffffu, S_, 1);
-            if (lane == 0) { Pe = 1.0f; Se = 0.0f; }
-            const float hin = fmaf(Pe, hc, Se);
+            if constexpr (HAS_Z) {
 #pragma unroll
-            for (int j = 0; j < LN_C; ++j) y[j] = fmaf(fmaf(pl[j], hin, hl[j]), ok ? Cv[n][j] : 0.0f, y[j]);
-            const float hend = __shfl_sync(0xffffffffu, fmaf(P, hc, S_), 31);
-            if (lane == r) carry_l[n] = hend;
-        }
-        if (ok) {
-            if (HAS_Z) {
-#pragma unroll
-                for (int j = 0; j < LN_C; ++j) y[j] *= silu_f(zv[j]);
+                for (int j = 0; j < C; ++j) y[j] *= silu_f(zv[j]);
             }
-            store_vec8<OUT_T>(ob + r * p.o_ds + (int64_t)step * TOK, y);
-        }
-        if (++r == nrows) { r = 0; ++step; }
+            const int64_t m0 = REV ? p.L - tok0 - C : tok0;      // lowest memory token of this lane's chunk
+            store_tokens<OUT_T, C, REV, FULL>(orow0 + r * p.o_ds + m0, y, nv);
+        };
+        if (full_step) body(std::true_type{}); else body(std::false_type{});
+        if (++r == w.nrows) { r = 0; ++step; }
     }
-    if (p.last && lane < nrows) {
+    __syncwarp();
+    if (p.last && lane < w.nrows) {
 #pragma unroll
-        for (int n = 0; n < NST; ++n) p.last[(b * p.dim + d0 + lane) * NST + n] = carry_l[n];
+        for (int n = 0; n < NST; ++n) p.last[(w.b * p.dim + w.d0 + lane) * NST + n] = rc[lane * RCF + NST + 2 + n];
     }
+}
+
+template <int NST, typename IN_T, typename OUT_T, int C, bool HAS_Z, bool SOFTPLUS, int NW>
+__global__ void __launch_bounds__((NW + 1) * 32) scan_lanes_kernel(const ScanParams p) {
+    using Cfg = LanesCfg<NST, IN_T, C, HAS_Z, NW>;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* base = smem_raw;
+    if (threadIdx.x == 0) {
+        uint64_t* bars = reinterpret_cast<uint64_t*>(base + NW * Cfg::WARP_BYTES);
+        for (int i = 0; i < NW * Cfg::NBARS; ++i) mbar_init(&bars[i], 1);
+        fence_mbar_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+    if (warp == NW) {
+        lanes_producer<NST, IN_T, C, HAS_Z, NW>(p, base, lane);
+        return;
+    }
+    const LanesWarp w = lanes_decode(p, (int64_t)blockIdx.x * NW + warp);
+    if (!w.valid) return;
+    const bool rev = w.g < 64 && ((p.rev_mask >> w.g) & 1);
+    if (rev) lanes_consumer<NST, IN_T, OUT_T, C, HAS_Z, SOFTPLUS, true, NW>(p, base, w, warp, lane);
+    else lanes_consumer<NST, IN_T, OUT_T, C, HAS_Z, SOFTPLUS, false, NW>(p, base, w, warp, lane);
 }
 
 // ============================================================================================
@@ -495,26 +633,47 @@ template <typename IN_T, typename OUT_T> static int launch_generic(const ScanPar
     return XP_OK;
 }
 
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+template <int NST, typename IN_T, typename OUT_T, int C, bool HAS_Z, bool SOFTPLUS, int NW>
+static int launch_lanes_cfg(const ScanParams& p, int64_t warps, cudaStream_t st) {
+    constexpr int smem = LanesCfg<NST, IN_T, C, HAS_Z, NW>::SMEM;
+    auto kern = scan_lanes_kernel<NST, IN_T, OUT_T, C, HAS_Z, SOFTPLUS, NW>;
+    XP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<(unsigned)ceil_div(warps, NW), (NW + 1) * 32, smem, st>>>(p);
+    XP_LAUNCH_CHECK("scan_lanes_kernel");
+    return XP_OK;
+}
+
+template <int NST, typename IN_T, typename OUT_T, int C> static int launch_lanes_c(const ScanParams& p, int64_t warps, cudaStream_t st) {
+    constexpr int NW = 4;
+    if (p.z) {
+        return p.softplus ? launch_lanes_cfg<NST, IN_T, OUT_T, C, true, true, NW>(p, warps, st)
+                          : launch_lanes_cfg<NST, IN_T, OUT_T, C, true, false, NW>(p, warps, st);
+    }
+    return p.softplus ? launch_lanes_cfg<NST, IN_T, OUT_T, C, false, true, NW>(p, warps, st)
+                      : launch_lanes_cfg<NST, IN_T, OUT_T, C, false, false, NW>(p, warps, st);
+}
+
 template <int NST, typename IN_T, typename OUT_T> static int launch_lanes(ScanParams p, cudaStream_t st) {
     const int64_t Dg = p.dim / p.groups;
     // rows per warp: share B/C across as many rows as possible while keeping >= ~2 waves of warps
     const int64_t target_warps = (int64_t)num_sms() * 16 * 2;
-    int rw = 8;
+    int rw = LN_MAXROWS;
     while (rw > 1 && p.batch * p.groups * ceil_div(Dg, rw) < target_warps) rw >>= 1;
     p.rows_per_warp = rw;
     const int64_t warps = p.batch * p.groups * ceil_div(Dg, rw);
-    const unsigned grid = (unsigned)ceil_div(warps, LN_WARPS);
-    if (p.z) {
-        constexpr int smem = LanesCfg<NST, IN_T, true>::SMEM;
-        XP_CUDA_OK(cudaFuncSetAttribute(scan_lanes_kernel<NST, IN_T, OUT_T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        scan_lanes_kernel<NST, IN_T, OUT_T, true><<<grid, LN_WARPS * 32, smem, st>>>(p);
-    } else {
-        constexpr int smem = LanesCfg<NST, IN_T, false>::SMEM;
-        XP_CUDA_OK(cudaFuncSetAttribute(scan_lanes_kernel<NST, IN_T, OUT_T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        scan_lanes_kernel<NST, IN_T, OUT_T, false><<<grid, LN_WARPS * 32, smem, st>>>(p);
+    // tokens per lane per step: 16 for single-state 16-bit inputs (halves the per-step overhead) unless the
+    // 512-token steps would pad the sequence more than 256-token steps do (L = 1280: 3 x 512 vs 5 x 256)
+    static const int c_override = env_int("XP_LANES_C", 0);   // tuning knob: 8 | 16
+    if constexpr (NST == 1 && sizeof(IN_T) == 2) {
+        const bool pads_more = ceil_div(p.L, 512) * 512 > ceil_div(p.L, 256) * 256;
+        if (c_override == 16 || (c_override != 8 && !pads_more)) return launch_lanes_c<NST, IN_T, OUT_T, 16>(p, warps, st);
     }
-    XP_LAUNCH_CHECK("scan_lanes_kernel");
-    return XP_OK;
+    return launch_lanes_c<NST, IN_T, OUT_T, 8>(p, warps, st);
 }
 
 template <int NST, typename IN_T, typename OUT_T, bool HAS_Z>
@@ -574,10 +733,12 @@ template <typename IN_T, typename OUT_T> static int dispatch(const ScanParams& p
                                   p.z ? p.z_bs : 0, p.z ? p.z_ds : 0};
     for (int64_t s : in_strides) vec_ok = vec_ok && (s % va == 0);
     vec_ok = vec_ok && (p.o_bs % vo == 0) && (p.o_ds % vo == 0);
-    if (vec_ok) {
+    const bool classic = p.rev_mask == 0 && p.u_gdiv == 1 && p.u_gs == (p.dim / p.groups) * p.u_ds;
+    vec_ok = vec_ok && (p.u_gs % va == 0);
+    if (vec_ok && p.dstate == 1) return launch_lanes<1, IN_T, OUT_T>(p, st);
+    if (vec_ok && p.dstate == 2) return launch_lanes<2, IN_T, OUT_T>(p, st);
+    if (vec_ok && classic) {
         switch (p.dstate) {
-            case 1: return launch_lanes<1, IN_T, OUT_T>(p, st);
-            case 2: return launch_lanes<2, IN_T, OUT_T>(p, st);
             case 4: return launch_rows<4, IN_T, OUT_T>(p, a->in_dtype, a->out_dtype, st);
             case 8: return launch_rows<8, IN_T, OUT_T>(p, a->in_dtype, a->out_dtype, st);
             case 16: return launch_rows<16, IN_T, OUT_T>(p, a->in_dtype, a->out_dtype, st);
@@ -613,6 +774,9 @@ extern "C" int xp_selective_scan_fwd(const xp_scan_args* a, xp_stream_t stream) 
     p.C_bs = a->C_batch_stride; p.C_gs = a->C_group_stride; p.C_ss = a->C_state_stride;
     p.z_bs = a->z_batch_stride; p.z_ds = a->z_dim_stride; p.o_bs = a->out_batch_stride; p.o_ds = a->out_dim_stride;
     p.softplus = a->delta_softplus; p.rows_per_warp = 1;
+    if (a->u_group_div > 0) { p.u_gdiv = a->u_group_div; p.u_gs = a->u_group_stride; }
+    else { p.u_gdiv = 1; p.u_gs = (a->dim / a->groups) * a->u_dim_stride; }
+    p.rev_mask = a->reverse_group_mask;
     cudaStream_t st = (cudaStream_t)stream;
     const int key = a->in_dtype * 4 + a->out_dtype;
     switch (key) {

@@ -23,10 +23,12 @@ import torch
 from . import _lib
 
 
-def _check_shapes(u, delta, A, B, C, D, z, delta_bias):
+def _check_shapes(u, delta, A, B, C, D, z, delta_bias, u_group_div=1):
     if u.dim() != 3:
         raise RuntimeError("u must have shape (batch, dim, seqlen)")
     batch, dim, L = u.shape
+    if u_group_div > 1:       # fused CrossScan addressing: u holds groups/u_group_div distinct sources
+        dim = dim * u_group_div
     if B.dim() == 3:
         B = B.unsqueeze(1)
     if C.dim() == 3:
@@ -58,6 +60,8 @@ def _check_shapes(u, delta, A, B, C, D, z, delta_bias):
         raise RuntimeError("delta_bias must be float32 with shape (delta_dim,)")
     if z is not None and tuple(z.shape) != (batch, dim, L):
         raise RuntimeError("z must have the same shape as u")
+    if u_group_div > 1 and (groups % u_group_div != 0 or ddim != dim):
+        raise RuntimeError("u_group_div must divide the number of groups and needs a full-width delta")
     return B, C, batch, dim, ddim, groups, N, L
 
 
@@ -68,10 +72,14 @@ def _last_contig(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 
 
 def scan_forward(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False, out_float=True,
-                 return_last_state=False, force_generic=False):
-    """One call of xp_selective_scan_fwd.  Returns (out, last_state or None)."""
+                 return_last_state=False, force_generic=False, u_group_div=1, reverse_group_mask=0):
+    """One call of xp_selective_scan_fwd.  Returns (out, last_state or None).
+
+    ``u_group_div`` / ``reverse_group_mask`` expose the fused-CrossScan addressing of the C ABI (xp_scan_args):
+    with ``u_group_div = q > 1`` u has shape (batch, dim / q, seqlen) and groups g, g+1, .. g+q-1 (g % q == 0) all read
+    source g / q; bit g of the mask makes group g run backwards through memory (its output stays unflipped)."""
     dev = _lib.require_cuda(u, delta, A, B, C, D, z, delta_bias)
-    B, C, batch, dim, ddim, groups, N, L = _check_shapes(u, delta, A, B, C, D, z, delta_bias)
+    B, C, batch, dim, ddim, groups, N, L = _check_shapes(u, delta, A, B, C, D, z, delta_bias, u_group_div)
     u, delta, B, C, z = map(_last_contig, (u, delta, B, C, z))
     A = A.contiguous()
     D = None if D is None else D.contiguous()
@@ -101,6 +109,10 @@ def scan_forward(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softp
     a.in_dtype, a.out_dtype = _lib.dtype_code(u), _lib.dtype_code(out)
     a.delta_softplus = int(bool(delta_softplus))
     a.force_generic = int(bool(force_generic))
+    if u_group_div > 1:
+        a.u_group_div = int(u_group_div)
+        a.u_group_stride = (dim // groups) * u.stride(1)
+    a.reverse_group_mask = int(reverse_group_mask)
     prof = _lib.scan_profile
     with torch.cuda.device(dev):
         if prof is not None:

@@ -136,6 +136,30 @@ XP_API int xp_merge_norm_gate(const void* ys, const float* gamma, const float* b
                        int64_t B, int64_t C, int64_t H, int64_t W, int32_t ys_dtype, int32_t out_dtype, float eps,
                        void* workspace, int64_t workspace_bytes, xp_stream_t stream);
 
+/* -- a3+a4+a5 fused: the copy-free SS2D core around xp_selective_scan_fwd ------------------
+ * Replaces cross_scan_fn + cross_merge_fn + out_norm of SS2D.forward_corev2 / forwardv0 (VMamba.py:603,632-646,
+ * :364-372) without materialising the four scan orders: the scan itself routes the directions
+ * (xp_scan_args.u_group_div = 2, reverse_group_mask = 0b1010) and these entry points provide the two layouts it
+ * reads and the one pass that consumes its four outputs.  Direction order everywhere below is
+ * [row-major forward (k=0), row-major backward (k=2), column-major forward (k=1), column-major backward (k=3)].
+ *
+ * xp_ss2d_pack:        x (B, D, H, W) -> xx (B, 2, D, L) = [x ; x^T] (x^T: token (h,w) at w*H+h), any dtype.
+ * xp_ss2d_dwconv_pack: the same preceded by SS2D's depth-wise 3x3 convolution (padding 1) and SiLU
+ *                      (VMamba.py:651-655): in is the CHANNEL-LAST in_proj output, channel c of token (h,w) at
+ *                      in[((b*H+h)*W+w)*in_token_stride + c], c < D; weight (D, 3, 3) fp32, bias (D) fp32 or NULL.
+ * xp_ss2d_merge_norm:  ys (B, 4, D, L) fp32, every plane in natural (unflipped) memory order, planes 0|1 row-major
+ *                      and 2|3 column-major -> out (B, H, W, D) = LayerNorm_D(ys0 + ys1 + (ys2 + ys3)^T) * gamma
+ *                      + beta [* zact], zact (B, H, W, D) in out_dtype or NULL.  H % 4 == W % 4 == 0, D <= 3072.
+ */
+XP_API int xp_ss2d_pack(const void* x, void* xx, int64_t B, int64_t D, int64_t H, int64_t W, int32_t dtype,
+                        xp_stream_t stream);
+XP_API int xp_ss2d_dwconv_pack(const void* in, const float* weight, const float* bias, void* xx, int64_t B, int64_t D,
+                               int64_t H, int64_t W, int64_t in_token_stride, int32_t dtype, int32_t silu,
+                               xp_stream_t stream);
+XP_API int xp_ss2d_merge_norm(const float* ys, const float* gamma, const float* beta, const void* zact, void* out,
+                              int64_t B, int64_t D, int64_t H, int64_t W, int32_t out_dtype, float eps,
+                              xp_stream_t stream);
+
 /* -- f2 (first "next" row): channel-last LayerNorm ---------------------------------------
  * Replaces the nn.LayerNorm calls around the SS2D block (VSSBlock.norm / norm2, patch-embed and downsample norms:
  * VMamba.py:1222-1234, :1405-1440).  x (rows, C) in in_dtype -> y (rows, C) in out_dtype; gamma/beta (C) fp32;

@@ -19,7 +19,8 @@ torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     pipe(o, t)
     torch.cuda.synchronize()
-ev = [e for e in prof.key_averages() if e.device_time_total > 0]
+ev = [e for e in prof.key_averages() if e.device_time_total > 0 and not e.key.startswith("aten::")
+      and str(e.device_type).endswith("CUDA")]   # kernels only (CPU-side op rows would double count)
 tot = sum(e.device_time_total for e in ev)
 print(f"total device time {tot/1e3:.2f} ms, {sum(e.count for e in ev)} launches")
 for e in sorted(ev, key=lambda e: -e.device_time_total)[:45]:

@@ -173,8 +173,11 @@ def gen_ss2d():
             m.out_norm.bias.copy_(0.1 * torch.randn_like(m.out_norm.bias))
             x = torch.randn(2, 6, 9, 16)
             y = m(x)
+            # a second input whose H, W are multiples of 4: the shape class the copy-free SS2D path covers
+            x4 = torch.randn(2, 12, 20, 16)
+            y4 = m(x4)
         arrs = {"sd." + k: v for k, v in m.state_dict().items()}
-        save(name, x=x, y=y, **arrs)
+        save(name, x=x, y=y, x4=x4, y4=y4, **arrs)
 
 
 # ------------------------------------------------------------------------------ heads + tail

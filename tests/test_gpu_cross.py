@@ -117,3 +117,79 @@ def test_layer_norm(C, dt_in, dt_out):
     out = layer_norm(x.to(DEV), w.to(DEV), b.to(DEV), 1e-5, dt_out)
     assert out.dtype == dt_out and out.shape == x.shape
     assert_close(out.float().cpu().numpy(), ref.numpy(), 1e-5 if dt_out == torch.float32 else 2e-3, f"layer_norm C={C}")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# copy-free SS2D core (xp_ss2d_pack / xp_ss2d_dwconv_pack / xp_ss2d_merge_norm + the scan's fused addressing)
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 5, 12, 20), (1, 3, 33, 70), (3, 16, 64, 80), (1, 2, 1, 7)])
+def test_ss2d_pack_exact(dtype, shape):
+    from xpoint_b200 import ss2d
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(*shape, generator=g).to(dtype).to(DEV)
+    xx = ss2d.ss2d_pack(x)
+    B, D, H, W = shape
+    assert torch.equal(xx[:, 0], x.reshape(B, D, H * W))
+    assert torch.equal(xx[:, 1], x.transpose(2, 3).reshape(B, D, H * W))
+    # the two layouts are exactly directions 0 and 1 of the reference CrossScan (csm_triton.py:22-29)
+    import xpoint_b200 as X
+    xs = X.cross_scan_fn(x, True, True, False, 0)
+    assert torch.equal(xx[:, 0], xs[:, 0]) and torch.equal(xx[:, 1], xs[:, 1])
+    assert torch.equal(xx[:, 0].flip(-1), xs[:, 2]) and torch.equal(xx[:, 1].flip(-1), xs[:, 3])
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-6), (torch.float16, 2e-3), (torch.bfloat16, 1.6e-2)])
+@pytest.mark.parametrize("B,H,W,D,Cin,bias", [(2, 12, 20, 16, 16, False), (1, 33, 70, 24, 48, True), (2, 64, 80, 96, 96, False),
+                                              (1, 16, 32, 40, 80, True), (1, 5, 3, 7, 7, True)])
+def test_ss2d_dwconv_pack_vs_torch(dtype, tol, B, H, W, D, Cin, bias):
+    """SS2D's depth-wise 3x3 conv + SiLU (VMamba.py:651-655) on the channel-last in_proj output, both layouts out."""
+    from xpoint_b200 import ss2d
+    g = torch.Generator().manual_seed(2)
+    xcl = torch.randn(B, H, W, Cin, generator=g).to(dtype).to(DEV)
+    w = (0.3 * torch.randn(D, 1, 3, 3, generator=g)).to(DEV)
+    b = (0.1 * torch.randn(D, generator=g)).to(DEV) if bias else None
+    xx = ss2d.ss2d_dwconv_pack(xcl[..., :D] if Cin != D else xcl, D, w, b, silu=True)
+    ref = torch.nn.functional.silu(torch.nn.functional.conv2d(xcl[..., :D].float().permute(0, 3, 1, 2), w, b, padding=1, groups=D))
+    np.testing.assert_allclose(xx[:, 0].float().cpu().numpy(), ref.reshape(B, D, H * W).cpu().numpy(), rtol=tol, atol=tol)
+    assert torch.equal(xx[:, 1].view(B, D, W, H), xx[:, 0].view(B, D, H, W).transpose(2, 3))
+
+
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("B,D,H,W,gate", [(2, 16, 12, 20, False), (1, 96, 16, 24, True), (2, 192, 8, 12, False), (1, 770, 8, 8, True),
+                                          (1, 1536, 4, 8, False), (1, 33, 20, 36, True)])
+def test_ss2d_merge_norm_vs_torch(out_dtype, B, D, H, W, gate):
+    """LayerNorm_D(ys0 + ys1 + (ys2 + ys3)^T) [* z]: CrossMerge (csm_triton.py:56-62) + out_norm (VMamba.py:644) with the
+    planes already in natural memory order."""
+    from xpoint_b200 import ss2d
+    g = torch.Generator().manual_seed(3)
+    L = H * W
+    ys = torch.randn(B, 4, D, L, generator=g).to(DEV)
+    gam = (1 + 0.1 * torch.randn(D, generator=g)).to(DEV)
+    bet = (0.1 * torch.randn(D, generator=g)).to(DEV)
+    z = torch.randn(B, H, W, D, generator=g).to(out_dtype).to(DEV) if gate else None
+    out = ss2d.ss2d_merge_norm(ys, H, W, gam, bet, z, 1e-5, out_dtype=out_dtype)
+    merged = (ys[:, 0] + ys[:, 1]).view(B, D, H, W) + (ys[:, 2] + ys[:, 3]).view(B, D, W, H).transpose(2, 3)
+    ref = torch.nn.functional.layer_norm(merged.permute(0, 2, 3, 1), (D,), gam, bet, 1e-5)
+    if gate:
+        ref = ref * z.float()
+    tol = 1e-5 if out_dtype == torch.float32 else 2e-3
+    np.testing.assert_allclose(out.float().cpu().numpy(), ref.cpu().numpy(), rtol=tol, atol=tol)
+    # and against the scan-order kernel the unfused path uses (flipped planes, reference direction order)
+    import xpoint_b200 as X
+    ys_ref_order = torch.stack([ys[:, 0], ys[:, 2], ys[:, 1].flip(-1), ys[:, 3].flip(-1)], dim=1).contiguous()
+    old = X.merge_norm_gate(ys_ref_order, H, W, gam, bet, z, 1e-5, out_dtype=out_dtype)
+    np.testing.assert_allclose(out.float().cpu().numpy(), old.float().cpu().numpy(), rtol=tol, atol=tol)
+
+
+def test_ss2d_fused_errors():
+    from xpoint_b200 import ss2d
+    ys = torch.randn(1, 4, 8, 6 * 9, device=DEV)
+    w = torch.ones(8, device=DEV)
+    with pytest.raises(RuntimeError):
+        ss2d.ss2d_merge_norm(ys, 6, 9, w, w)                     # H, W must be multiples of 4
+    with pytest.raises(RuntimeError):
+        ss2d.ss2d_merge_norm(ys.half(), 6, 9, w, w)              # fp32 planes only
+    with pytest.raises(RuntimeError):
+        ss2d.ss2d_pack(torch.randn(1, 2, 4, 4))                  # no CPU path
+    assert ss2d.ss2d_pack(torch.randn(0, 2, 4, 4, device=DEV)).shape == (0, 2, 2, 16)

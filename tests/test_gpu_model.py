@@ -43,6 +43,50 @@ def test_ss2d_block_golden(name, kw):
     with torch.no_grad():
         y = m(torch.from_numpy(g["x"]).to(DEV))
     assert_close(y.cpu().numpy(), g["y"], FP32_REL, name)
+    # 12 x 20 tokens: the shape class of the copy-free path (H, W multiples of 4); d_state <= 2 takes it
+    assert m._use_fused(12, 20, torch.float32) == (kw["d_state"] <= 2)
+    with torch.no_grad():
+        y4 = m(torch.from_numpy(g["x4"]).to(DEV))
+        m.disable_fused = True
+        y4u = m(torch.from_numpy(g["x4"]).to(DEV))
+    assert_close(y4.cpu().numpy(), g["y4"], FP32_REL, name + " 12x20 (fused where supported)")
+    assert_close(y4u.cpu().numpy(), g["y4"], FP32_REL, name + " 12x20 (CrossScan/CrossMerge kernels)")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("ft,N,ratio", [("v05_noz", 1, 1.0), ("v05", 2, 2.0), ("v05_nozact", 1, 2.0), ("v05_oact", 1, 1.0)])
+def test_ss2d_fused_matches_unfused(dtype, ft, N, ratio):
+    """Copy-free path vs the CrossScan -> scan -> CrossMerge path of the same module at an XPoint stage shape."""
+    import xpoint_b200 as X
+    torch.manual_seed(0)
+    m = X.SS2D(d_model=48, d_state=N, ssm_ratio=ratio, forward_type=ft, conv_bias=(ft != "v05_noz")).to(DEV).eval()
+    x = torch.randn(2, 32, 40, 48, device=DEV)
+    with torch.no_grad(), torch.autocast("cuda", dtype=dtype, enabled=dtype != torch.float32):
+        assert m._use_fused(32, 40, dtype)
+        y = m(x)
+        m.disable_fused = True
+        yu = m(x)
+    assert y.dtype == yu.dtype
+    assert_close(y.float().cpu().numpy(), yu.float().cpu().numpy(), 2e-5 if dtype == torch.float32 else 1e-2, f"{ft} {dtype}")
+
+
+@pytest.mark.parametrize("H,W,C", [(128, 160, 96), (64, 80, 192), (32, 40, 384), (16, 20, 768)])
+def test_ss2d_fp16_autocast_at_xpoint_stage_shapes(H, W, C):
+    """The four stage shapes of preset E at 512x640: fp16 autocast (the reference's
+    mixed_precision path, XPoint.py:182) against fp32, on both SS2D paths.  Catches shape-dependent library
+    behaviour as well: cuDNN's fp16 depth-wise conv was wrong at (16, 20, 768), which is why SS2D runs its own."""
+    import xpoint_b200 as X
+    torch.manual_seed(0)
+    m = X.SS2D(d_model=C, d_state=1, ssm_ratio=1.0, forward_type="v05_noz", conv_bias=False).to(DEV).eval()
+    x = torch.randn(2, H, W, C, device=DEV)
+    with torch.no_grad():
+        ref = m(x)
+        for fused in (True, False):
+            m.disable_fused = not fused
+            with torch.autocast("cuda", dtype=torch.float16):
+                y = m(x)
+            assert y.dtype == torch.float16
+            assert_close(y.float().cpu().numpy(), ref.cpu().numpy(), 1e-2, f"fp16 fused={fused} {H}x{W}x{C}")
 
 
 @pytest.mark.parametrize("tag", ["E", "V"])

@@ -1,0 +1,79 @@
+"""Copy-free SS2D core: the host side of xp_ss2d_pack / xp_ss2d_dwconv_pack / xp_ss2d_merge_norm.
+
+The reference's SS2D core (VMamba.py:493-646 ``forward_corev2``, :305-374 ``forwardv0``) materialises the four scan
+orders with CrossScan, scans them, and sums them back with CrossMerge.  Here the selective-scan kernel routes the
+directions itself (``scan_forward(..., u_group_div=2, reverse_group_mask=0b1010)``): it reads ONE copy of the
+activations in row-major order and one in column-major order, walks each forwards and backwards, and leaves the four
+outputs in natural memory order, so CrossScan shrinks to ``[x ; x^T]`` and CrossMerge + out_norm (+ gate) to one pass.
+
+Direction order used throughout the fused path: ``FUSED_ORDER = (0, 2, 1, 3)`` i.e. [row forward, row backward,
+column forward, column backward] in the reference's numbering k (csm_triton.py:22-29).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+FUSED_ORDER = (0, 2, 1, 3)
+REVERSE_MASK = 0b1010
+
+
+def ss2d_pack(x: torch.Tensor) -> torch.Tensor:
+    """x (B, D, H, W) -> xx (B, 2, D, H*W) = [x ; x^T]."""
+    dev = _lib.require_cuda(x)
+    x = x.contiguous()
+    B, D, H, W = x.shape
+    xx = torch.empty((B, 2, D, H * W), dtype=x.dtype, device=dev)
+    if xx.numel():
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().xp_ss2d_pack(_lib.ptr(x), _lib.ptr(xx), B, D, H, W, _lib.dtype_code(x), _lib.stream_ptr(dev)))
+        _lib.count_launches(1)
+    return xx
+
+
+def ss2d_dwconv_pack(x_cl: torch.Tensor, D: int, weight: torch.Tensor, bias, silu: bool = True) -> torch.Tensor:
+    """x_cl (B, H, W, >=D) channel-last (a view of the in_proj output is fine: only the token stride must be uniform)
+    -> xx (B, 2, D, H*W) = [act(dwconv3x3(x)) ; its transpose].  weight (D, 1, 3, 3) fp32, bias (D) fp32 or None."""
+    dev = _lib.require_cuda(x_cl, weight, bias)
+    B, H, W, Cin = x_cl.shape
+    if x_cl.stride(3) != 1 or x_cl.stride(1) != W * x_cl.stride(2) or x_cl.stride(0) != H * x_cl.stride(1):
+        x_cl = x_cl.contiguous()
+    if tuple(weight.shape[-2:]) != (3, 3) or weight.shape[0] != D or D > Cin:
+        raise RuntimeError("ss2d_dwconv_pack expects a depth-wise 3x3 weight of shape (D, 1, 3, 3)")
+    xx = torch.empty((B, 2, D, H * W), dtype=x_cl.dtype, device=dev)
+    if xx.numel():
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().xp_ss2d_dwconv_pack(_lib.ptr(x_cl), _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(xx), B, D, H, W,
+                                                      x_cl.stride(2), _lib.dtype_code(x_cl), int(bool(silu)),
+                                                      _lib.stream_ptr(dev)))
+        _lib.count_launches(1)
+    return xx
+
+
+def ss2d_merge_norm(ys: torch.Tensor, H: int, W: int, weight: torch.Tensor, bias: torch.Tensor, zact=None, eps=1e-5,
+                    out_dtype=None) -> torch.Tensor:
+    """ys (B, 4, D, L) fp32, planes in FUSED_ORDER and natural memory order -> (B, H, W, D)."""
+    dev = _lib.require_cuda(ys, weight, bias, zact)
+    B, K, D, L = ys.shape
+    if K != 4 or L != H * W or ys.dtype != torch.float32:
+        raise RuntimeError("ss2d_merge_norm expects fp32 ys of shape (B, 4, D, H*W)")
+    ys = ys.contiguous()
+    out_dtype = out_dtype or (zact.dtype if zact is not None else ys.dtype)
+    out = torch.empty((B, H, W, D), dtype=out_dtype, device=dev)
+    if zact is not None:
+        zact = zact.contiguous()
+        if zact.dtype != out_dtype or zact.numel() != out.numel():
+            raise RuntimeError("zact must match the output dtype and shape (B, H, W, D)")
+    if out.numel():
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().xp_ss2d_merge_norm(_lib.ptr(ys), _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(zact),
+                                                     _lib.ptr(out), B, D, H, W, _lib.dtype_code(out), float(eps),
+                                                     _lib.stream_ptr(dev)))
+        _lib.count_launches(1)
+    return out
+
+
+def fused_supported(H: int, W: int, D: int, d_state: int) -> bool:
+    """Shapes the copy-free path covers (the rest takes the CrossScan -> scan -> CrossMerge kernels)."""
+    return H % 4 == 0 and W % 4 == 0 and D <= 3072 and d_state <= 2

@@ -20,8 +20,9 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import ss2d as _ss2d
 from .cross_scan import cross_scan_fn, layer_norm, merge_norm_gate
-from .selective_scan import selective_scan_fn
+from .selective_scan import scan_forward, selective_scan_fn
 
 
 class Permute(nn.Module):
@@ -196,24 +197,89 @@ class SS2D(nn.Module):
         return merge_norm_gate(ys.view(B, K, D, L), H, W, self.out_norm.weight, self.out_norm.bias, zact,
                                self.out_norm.eps, out_dtype=x.dtype)
 
+    # -------------------------------------------------------------------------------------------------------
+    def _fused_weights(self, batch: int, dtype: torch.dtype):
+        """Projection / scan parameters re-ordered to ss2d.FUSED_ORDER, cast once and cached (inference: the
+        parameters are static; the cache is keyed on their versions so in-place updates invalidate it)."""
+        params = (self.x_proj_weight, self.dt_projs_weight, self.dt_projs_bias, self.A_logs, self.Ds, self.out_norm.weight,
+                  self.out_norm.bias) + ((self.conv2d.weight,) if self.with_dconv else ())
+        key = (batch, dtype, self.x_proj_weight.device) + tuple((q.data_ptr(), q._version) for q in params)
+        cache = getattr(self, "_fw_cache", None)
+        if cache is not None and cache[0] == key:
+            return cache[1]
+        K, D, N, R = self.k_group, self.d_inner, self.d_state, self.dt_rank
+        order = list(_ss2d.FUSED_ORDER)
+        with torch.no_grad():
+            wx = self.x_proj_weight.detach()[order].reshape(1, 2, 2 * (R + 2 * N), D).to(dtype)
+            wdt = self.dt_projs_weight.detach()[order].reshape(1, 2, 2, D, R).to(dtype)
+            w = dict(
+                wx=wx.expand(batch, -1, -1, -1).contiguous(),                     # (B, 2, 2(R+2N), D)
+                wdt=wdt.expand(batch, -1, -1, -1, -1).contiguous(),               # (B, 2, 2, D, R)
+                A=(-self.A_logs.detach().float().exp()).view(K, D, N)[order].reshape(K * D, N).contiguous(),
+                Ds=self.Ds.detach().float().view(K, D)[order].reshape(-1).contiguous(),
+                dt_bias=self.dt_projs_bias.detach().float()[order].reshape(-1).contiguous(),
+                norm_w=self.out_norm.weight.detach().float().contiguous(),
+                norm_b=self.out_norm.bias.detach().float().contiguous(),
+            )
+            if self.with_dconv:
+                w["conv_w"] = self.conv2d.weight.detach().float().contiguous()
+                w["conv_b"] = None if self.conv2d.bias is None else self.conv2d.bias.detach().float().contiguous()
+        self._fw_cache = (key, w)
+        return w
+
+    def forward_core_fused(self, xx: torch.Tensor, H: int, W: int, zact=None, out_dtype=None) -> torch.Tensor:
+        """xx (B, 2, d_inner, L) = [x ; x^T] -> (B, H, W, d_inner).  Same math as ``forward_core`` without the
+        CrossScan / CrossMerge copies: both projections run directly on the two layouts, the scan kernel routes the
+        four directions, and one pass merges + normalises (+ gates)."""
+        B, _, D, L = xx.shape
+        K, N, R = self.k_group, self.d_state, self.dt_rank
+        w = self._fused_weights(B, xx.dtype)
+        x_dbl = torch.matmul(w["wx"], xx)                                          # (B, 2, 2(R+2N), L)
+        x_dbl = x_dbl.view(B, 2, 2, R + 2 * N, L)
+        dts = torch.matmul(w["wdt"], x_dbl[:, :, :, :R])                           # (B, 2, 2, D, L)
+        x_dbl = x_dbl.view(B, K, R + 2 * N, L)
+        ys, _ = scan_forward(xx.view(B, 2 * D, L), dts.view(B, K * D, L), w["A"], x_dbl[:, :, R:R + N], x_dbl[:, :, R + N:],
+                             w["Ds"], None, w["dt_bias"], True, True, u_group_div=2,
+                             reverse_group_mask=_ss2d.REVERSE_MASK)               # (B, 4*D, L) fp32, natural order
+        return _ss2d.ss2d_merge_norm(ys.view(B, K, D, L), H, W, w["norm_w"], w["norm_b"], zact, self.out_norm.eps,
+                                     out_dtype=out_dtype or xx.dtype)
+
+    def _use_fused(self, H: int, W: int, dtype: torch.dtype) -> bool:
+        return (_ss2d.fused_supported(H, W, self.d_inner, self.d_state) and (not self.force_fp32 or dtype == torch.float32)
+                and (self.family == "v0" or self.oflex or dtype == torch.float32) and not getattr(self, "disable_fused", False))
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """x (B, H, W, d_model) -> (B, H, W, d_model)   (forwardv0 VMamba.py:305-374, forwardv2 :648-664)."""
+        """x (B, H, W, d_model) -> (B, H, W, d_model)   (forwardv0 VMamba.py:305-374, forwardv2 :648-664).
+
+        in_proj / out_proj stay cuBLAS GEMMs.  The depth-wise 3x3 convolution + SiLU run on xp_ss2d_dwconv_pack, which
+        reads the channel-last in_proj output directly and emits the channel-first layouts the scan needs (no permute
+        copy, no cuDNN call: cuDNN's fp16 depth-wise kernel also returned wrong values for 768 channels at 16x20 on
+        B200, scripts/debug_unfused.py)."""
         x = self.in_proj(x)
-        z = None
+        Bn, H, W, _ = x.shape
+        D = self.d_inner
+        zact = None
         if not self.disable_z:
-            x, z = x.chunk(2, dim=-1)
-            if not self.disable_z_act:
-                z = self.act(z)
-        x = x.permute(0, 3, 1, 2).contiguous()
-        if self.with_dconv:
-            x = self.conv2d(x)
-        x = self.act(x)
-        if isinstance(self.out_act, nn.Identity) and z is not None:
-            y = self.forward_core(x, zact=z.contiguous().to(x.dtype))
+            zact = x[..., D:]
+            zact = (zact if self.disable_z_act else self.act(zact)).contiguous()
+        fused = self._use_fused(H, W, x.dtype)
+        if self.with_dconv and self.conv2d.kernel_size == (3, 3) and isinstance(self.act, nn.SiLU):
+            w = self._fused_weights(Bn, x.dtype)
+            xx = _ss2d.ss2d_dwconv_pack(x, D, w["conv_w"], w["conv_b"], silu=True)          # (B, 2, D, L) = [x ; x^T]
+            xc = None if fused else xx[:, 0].view(Bn, D, H, W)
         else:
-            y = self.out_act(self.forward_core(x))
-            if z is not None:
-                y = y * z
+            xc = x[..., :D].permute(0, 3, 1, 2).contiguous()
+            if self.with_dconv:
+                xc = self.conv2d(xc)
+            xc = self.act(xc)
+            xx = _ss2d.ss2d_pack(xc) if fused else None
+        core = (lambda z: self.forward_core_fused(xx, H, W, zact=z)) if fused else (lambda z: self.forward_core(xc, zact=z))
+        if isinstance(self.out_act, nn.Identity):
+            y = core(zact)
+        else:
+            y = self.out_act(core(None))
+            if zact is not None:
+                y = y * zact
         return self.out_proj(y)
 
 

@@ -459,168 +459,251 @@ __global__ void __launch_bounds__((NW + 1) * 32) scan_lanes_kernel(const ScanPar
 }
 
 // ============================================================================================
-// rows kernel (dstate 4 | 8 | 16), warp-private TMA pipelines
+// rows kernel (dstate 4 | 8 | 16)
 // ============================================================================================
-constexpr int RT_ROWS = 32;      // channel rows per warp (one per lane)
-constexpr int RT_STAGES = 2;
-constexpr int RT_WARPS = 2;      // warps per CTA (independent pipelines)
+// At dstate 16 the scan is bound by the MUFU pipe and FP32 issue, not HBM: one ex2 and four FP32
+// ops per (token, state) is the minimum, so the design spends nothing else per state and makes the per-token work
+// (softplus, delta*u, D*u, stores) cooperative.
+//   * a channel row is owned by TWO adjacent lanes; lane half hf keeps the states n with n % 2 == hf in registers and
+//     runs their recurrences sequentially (no redundant scan arithmetic).  A warp covers 16 rows, a CTA 4 warps = 64
+//     rows of one (batch, group) plus one producer warp.
+//   * per 8-token step the lanes of a pair each evaluate softplus / delta*u for 4 of the 8 tokens and swap them with
+//     SHFL, so the two MUFU ops of softplus are paid once per token, not once per lane.
+//   * operands arrive by TMA: per-warp rings of u / delta [/ z] tiles [16 rows x 128 B] and ONE CTA-wide ring of
+//     B / C tiles [dstate x 128 B] (shared by the 64 rows), all in 128B-swizzled shared memory so that the 16-byte
+//     reads of a pair-interleaved warp are conflict-free; completion through mbarriers, refill by the producer warp.
+//   * y: the pair's partial sums are exchanged with SHFL and each lane stores its 4 tokens (32 contiguous bytes per
+//     row per step); no staging tile.
+//   * reversed groups / shared-u addressing as in the lanes kernel (tile walk mirrored, elements reversed in registers).
+constexpr int RT_ROWS = 16;      // channel rows per consumer warp (two lanes each)
+constexpr int RT_NW = 4;         // consumer warps per CTA
+constexpr int RT_STAGES = 3;     // u/delta ring depth per warp
+constexpr int RT_BCS = 3;        // B/C ring depth per CTA
 
-template <int NST, typename IN_T, typename OUT_T, bool HAS_Z> struct RowsCfg {
-    static constexpr int VEC = 16 / (int)sizeof(IN_T);       // tokens per 16-byte chunk
-    static constexpr int T = 8 * VEC;                         // tokens per tile (128 B per row)
-    static constexpr int TILE_ROW = RT_ROWS * 128;            // u / delta / z tile bytes
-    static constexpr int TILE_BC = NST * 128;
-    static constexpr int STAGE = TILE_ROW * (HAS_Z ? 3 : 2) + 2 * TILE_BC;
-    static constexpr int YBOX_TOK = 128 / (int)sizeof(OUT_T); // tokens per y box
-    static constexpr int YBOXES = T / YBOX_TOK;               // 1, or 2 for 16-bit in -> fp32 out
-    static constexpr int YBYTES = YBOXES * TILE_ROW;
-    static constexpr int WARP_BYTES = RT_STAGES * STAGE + YBYTES;  // multiple of 1024 for NST in {4,8,16}
-    static constexpr int SMEM = RT_WARPS * WARP_BYTES + 1024 /*align slack*/ + RT_WARPS * RT_STAGES * 8;
+template <int NST, typename IN_T, bool HAS_Z> struct RowsCfg {
+    static constexpr int VEC = 16 / (int)sizeof(IN_T);        // tokens per 16-byte chunk
+    static constexpr int T = 8 * VEC;                          // tokens per tile (128 B per row)
+    static constexpr int TILE = RT_ROWS * 128;                 // u / delta / z tile bytes (2 KiB)
+    static constexpr int ITEM = TILE * (HAS_Z ? 3 : 2);
+    static constexpr int TB = (NST * 128 + 1023) / 1024 * 1024;   // B (or C) tile bytes, 1 KiB granules keep the swizzle phase
+    static constexpr int BC = 2 * TB;
+    static constexpr int RING = RT_STAGES * ITEM;
+    static constexpr int NBARS = RT_NW * 2 * RT_STAGES + 2 * RT_BCS;
+    static constexpr int SMEM = RT_NW * RING + RT_BCS * BC + NBARS * 8 + 1024 /*align slack*/;
 };
 
-__device__ __forceinline__ uint32_t swz128(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
-
-template <typename IN_T> __device__ __forceinline__ void lds_chunk(const uint8_t* p, float (&f)[16 / sizeof(IN_T)]);
-template <> __device__ __forceinline__ void lds_chunk<float>(const uint8_t* p, float (&f)[4]) {
-    const float4 v = *reinterpret_cast<const float4*>(p);
-    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
-}
-template <> __device__ __forceinline__ void lds_chunk<__half>(const uint8_t* p, float (&f)[8]) {
-    VecIO<__half, 8>::widen(*reinterpret_cast<const uint4*>(p), f);
-}
-template <> __device__ __forceinline__ void lds_chunk<__nv_bfloat16>(const uint8_t* p, float (&f)[8]) {
-    VecIO<__nv_bfloat16, 8>::widen(*reinterpret_cast<const uint4*>(p), f);
-}
-
-template <int NST, typename IN_T, typename OUT_T, bool HAS_Z>
-__global__ void __launch_bounds__(RT_WARPS * 32)
-scan_rows_tma_kernel(const ScanParams p, const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_d,
-                     const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_B,
-                     const __grid_constant__ CUtensorMap map_C, const __grid_constant__ CUtensorMap map_y) {
-    using Cfg = RowsCfg<NST, IN_T, OUT_T, HAS_Z>;
-    constexpr int VEC = Cfg::VEC, T = Cfg::T;
-    extern __shared__ uint8_t smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* wbase = base + warp * Cfg::WARP_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(base + RT_WARPS * Cfg::WARP_BYTES) + warp * RT_STAGES;
-    uint8_t* ybuf = wbase + RT_STAGES * Cfg::STAGE;
-
-    const int64_t Dg = p.dim / p.groups;
-    const int64_t rb_per_group = (Dg + RT_ROWS - 1) / RT_ROWS;
-    const int64_t wid = (int64_t)blockIdx.x * RT_WARPS + warp;
-    if (wid >= p.batch * p.groups * rb_per_group) return;   // whole warp exits together
-    const int rb = (int)(wid % rb_per_group);
-    const int g = (int)((wid / rb_per_group) % p.groups);
-    const int b = (int)(wid / (rb_per_group * p.groups));
-    const int dg0 = rb * RT_ROWS;                 // row offset inside the group
-    const bool row_ok = dg0 + lane < Dg;
-    const int64_t d = (int64_t)g * Dg + dg0 + lane;
-
-    float A2[NST], h[NST];
+// 8 consecutive scan-order tokens (group c8 of the tile) of one tile row, fp32, from 128B-swizzled shared memory
+template <typename IN_T, bool REV> __device__ __forceinline__ void lds_group8(uint32_t tile_saddr, int row, int c8, float (&f)[8]) {
+    constexpr int VEC = 16 / (int)sizeof(IN_T), NCH = 8 / VEC;
 #pragma unroll
-    for (int n = 0; n < NST; ++n) { A2[n] = row_ok ? p.A[d * NST + n] * kLog2e : 0.0f; h[n] = 0.0f; }
+    for (int k = 0; k < NCH; ++k) {
+        const int ch = REV ? 7 - (c8 * NCH + k) : c8 * NCH + k;
+        float w[VEC];
+        widen16<IN_T>(lds128(tile_saddr + row * 128 + ((ch ^ (row & 7)) << 4)), w);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) f[k * VEC + i] = w[REV ? VEC - 1 - i : i];
+    }
+}
+
+template <int NST, typename IN_T, typename OUT_T, bool HAS_Z, bool SOFTPLUS, bool REV>
+__device__ __forceinline__ void rows_consumer(const ScanParams& p, uint32_t sbase, int warp, int lane, int64_t b, int64_t g,
+                                              int64_t dg0) {
+    using Cfg = RowsCfg<NST, IN_T, HAS_Z>;
+    constexpr int T = Cfg::T, SPL = NST / 2;
+    const uint32_t ring = sbase + warp * Cfg::RING;
+    const uint32_t bcring = sbase + RT_NW * Cfg::RING;
+    const uint32_t bars = bcring + RT_BCS * Cfg::BC;
+    const uint32_t full = bars + warp * 2 * RT_STAGES * 8, empty = full + RT_STAGES * 8;
+    const uint32_t bcfull = bars + RT_NW * 2 * RT_STAGES * 8, bcempty = bcfull + RT_BCS * 8;
+
+    const int r = lane >> 1, hf = lane & 1;
+    const int64_t Dg = p.dim / p.groups;
+    const bool row_ok = dg0 + r < Dg;
+    const int64_t d = g * Dg + dg0 + r;
+    float A2[SPL], h[SPL];
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) { A2[i] = row_ok ? p.A[d * NST + 2 * i + hf] * kLog2e : 0.0f; h[i] = 0.0f; }
     const float bias = (row_ok && p.bias) ? p.bias[d] : 0.0f;
     const float Dv = (row_ok && p.D) ? p.D[d] : 0.0f;
+    const float Dm0 = hf == 0 ? Dv : 0.0f, Dm1 = hf == 1 ? Dv : 0.0f;   // D*u enters the pair sum exactly once
+    const int src0 = lane & ~1, src1 = lane | 1;
+    OUT_T* orow = (OUT_T*)p.out + b * p.o_bs + d * p.o_ds;
 
     const int ntiles = (int)((p.L + T - 1) / T);
-    auto issue = [&](int tile) {   // lane 0 only
-        const int s = tile % RT_STAGES;
-        uint8_t* st = wbase + s * Cfg::STAGE;
-        mbar_arrive_expect_tx(&bars[s], Cfg::STAGE);
-        const int t0 = tile * T;
-        tma_load_4d(st, &map_u, &bars[s], t0, dg0, g, b);
-        tma_load_4d(st + Cfg::TILE_ROW, &map_d, &bars[s], t0, dg0, g, b);
-        uint8_t* nx = st + 2 * Cfg::TILE_ROW;
-        if (HAS_Z) { tma_load_4d(nx, &map_z, &bars[s], t0, dg0, g, b); nx += Cfg::TILE_ROW; }
-        tma_load_4d(nx, &map_B, &bars[s], t0, 0, g, b);
-        tma_load_4d(nx + Cfg::TILE_BC, &map_C, &bars[s], t0, 0, g, b);
-    };
-    if (lane == 0) {
-        for (int s = 0; s < RT_STAGES; ++s) mbar_init(&bars[s], 1);
-        fence_mbar_init();
-        fence_proxy_async();
-        for (int s = 0; s < RT_STAGES && s < ntiles; ++s) issue(s);
-    }
-    __syncwarp();
-
     for (int tile = 0; tile < ntiles; ++tile) {
-        const int s = tile % RT_STAGES;
-        const uint32_t parity = (uint32_t)((tile / RT_STAGES) & 1);
-        mbar_wait(&bars[s], parity);
-        const uint8_t* st = wbase + s * Cfg::STAGE;
-        const uint8_t* su = st;
-        const uint8_t* sd = st + Cfg::TILE_ROW;
-        const uint8_t* sz = st + 2 * Cfg::TILE_ROW;
-        const uint8_t* sB = st + (HAS_Z ? 3 : 2) * Cfg::TILE_ROW;
-        const uint8_t* sC = sB + Cfg::TILE_BC;
-        // the previous tile's TMA store must have finished READING ybuf before we overwrite it
-        if (lane == 0) tma_store_wait_read<0>();
-        __syncwarp();
-        const int valid = (int)min((int64_t)T, p.L - (int64_t)tile * T);
+        const int slot = tile % RT_STAGES, bslot = tile % RT_BCS;
+        mbar_wait_s(full + slot * 8, (uint32_t)(tile / RT_STAGES) & 1u);
+        mbar_wait_s(bcfull + bslot * 8, (uint32_t)(tile / RT_BCS) & 1u);
+        const uint32_t su = ring + slot * Cfg::ITEM, sd = su + Cfg::TILE, sz = sd + Cfg::TILE;
+        const uint32_t sB = bcring + bslot * Cfg::BC, sC = sB + Cfg::TB;
+        const int valid = (int)min((int64_t)T, p.L - (int64_t)tile * T);   // multiple of 8 (host-checked)
 #pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
-            if (c * VEC >= valid) break;   // L % VEC == 0 (host-checked): chunks are all-or-nothing
-            float uv[VEC], dv[VEC], y[VEC];
-            lds_chunk<IN_T>(su + swz128(lane, c), uv);
-            lds_chunk<IN_T>(sd + swz128(lane, c), dv);
+        for (int c8 = 0; c8 * 8 < valid; ++c8) {
+            float u8[8], d8[8];
+            lds_group8<IN_T, REV>(su, r, c8, u8);
+            lds_group8<IN_T, REV>(sd, r, c8, d8);
+            // this lane evaluates tokens 2j + hf, then the pair swaps: 4 softplus per lane instead of 8
+            float dl[8], du[8], yp[8];
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                dv[j] = delta_act(dv[j], bias, p.softplus);
-                y[j] = Dv * uv[j];
-                uv[j] *= dv[j];
+            for (int j = 0; j < 4; ++j) {
+                const float uo = hf ? u8[2 * j + 1] : u8[2 * j];
+                const float x = (hf ? d8[2 * j + 1] : d8[2 * j]) + bias;
+                const float dlo = SOFTPLUS ? softplus_f(x) : x;
+                const float duo = dlo * uo;
+                dl[2 * j] = __shfl_sync(0xffffffffu, dlo, src0);
+                dl[2 * j + 1] = __shfl_sync(0xffffffffu, dlo, src1);
+                du[2 * j] = __shfl_sync(0xffffffffu, duo, src0);
+                du[2 * j + 1] = __shfl_sync(0xffffffffu, duo, src1);
+                yp[2 * j] = Dm0 * uo;
+                yp[2 * j + 1] = Dm1 * uo;
             }
 #pragma unroll
-            for (int n = 0; n < NST; ++n) {
-                float bv[VEC], cv[VEC];
-                lds_chunk<IN_T>(sB + n * 128 + c * 16, bv);   // broadcast reads
-                lds_chunk<IN_T>(sC + n * 128 + c * 16, cv);
+            for (int i = 0; i < SPL; ++i) {
+                float bv[8], cv[8];
+                lds_group8<IN_T, REV>(sB, 2 * i + hf, c8, bv);
+                lds_group8<IN_T, REV>(sC, 2 * i + hf, c8, cv);
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) {
-                    const float a = ex2_approx(dv[j] * A2[n]);
-                    h[n] = fmaf(a, h[n], uv[j] * bv[j]);
-                    y[j] = fmaf(h[n], cv[j], y[j]);
+                for (int t = 0; t < 8; ++t) {
+                    const float a = ex2_approx(dl[t] * A2[i]);
+                    h[i] = fmaf(a, h[i], du[t] * bv[t]);
+                    yp[t] = fmaf(h[i], cv[t], yp[t]);
                 }
             }
-            if (HAS_Z) {
-                float zv[VEC];
-                lds_chunk<IN_T>(sz + swz128(lane, c), zv);
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) y[j] *= silu_f(zv[j]);
-            }
-            // y chunk -> swizzled staging tile(s)
+            const int64_t tok = (int64_t)tile * T + c8 * 8;          // first scan-order token of the group
             if constexpr (sizeof(OUT_T) == 4) {
+                // lane hf finishes tokens 4*hf .. 4*hf+3: send the partner's half, keep mine
+                float tot[4];
 #pragma unroll
-                for (int q = 0; q < VEC / 4; ++q) {
-                    const int tok = c * VEC + q * 4;
-                    uint8_t* dst = ybuf + (tok / 32) * Cfg::TILE_ROW + swz128(lane, (tok % 32) / 4);
-                    *reinterpret_cast<float4*>(dst) = make_float4(y[q * 4], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
+                for (int j = 0; j < 4; ++j) {
+                    const float send = hf ? yp[j] : yp[4 + j], keep = hf ? yp[4 + j] : yp[j];
+                    tot[j] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+                }
+                if constexpr (HAS_Z) {
+                    float z8[8];
+                    lds_group8<IN_T, REV>(sz, r, c8, z8);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) tot[j] *= silu_f(hf ? z8[4 + j] : z8[j]);
+                }
+                if (row_ok) {
+                    const int64_t t4 = tok + 4 * hf;
+                    float m[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) m[REV ? 3 - j : j] = tot[j];
+                    VecIO<float, 4>::store(reinterpret_cast<float*>(orow) + (REV ? p.L - t4 - 4 : t4), m);
                 }
             } else {
-                static_assert(sizeof(OUT_T) == 4 || VEC == 8, "16-bit output implies 16-bit input");
-                uint4 v;
-                OUT_T* hp = reinterpret_cast<OUT_T*>(&v);
+                float tot[8];
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) hp[j] = from_f32<OUT_T>(y[j]);
-                *reinterpret_cast<uint4*>(ybuf + swz128(lane, c)) = v;
+                for (int t = 0; t < 8; ++t) tot[t] = yp[t] + __shfl_xor_sync(0xffffffffu, yp[t], 1);
+                if constexpr (HAS_Z) {
+                    float z8[8];
+                    lds_group8<IN_T, REV>(sz, r, c8, z8);
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) tot[t] *= silu_f(z8[t]);
+                }
+                if (row_ok && hf == 0) {
+                    float m[8];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) m[REV ? 7 - t : t] = tot[t];
+                    VecIO<OUT_T, 8>::store(orow + (REV ? p.L - tok - 8 : tok), m);
+                }
             }
         }
-        fence_proxy_async();   // make this lane's generic-proxy smem writes visible to the TMA store
-        __syncwarp();
-        if (lane == 0) {
-            const int t0 = tile * T;
-#pragma unroll
-            for (int q = 0; q < Cfg::YBOXES; ++q)
-                if (q * Cfg::YBOX_TOK < valid) tma_store_4d(&map_y, ybuf + q * Cfg::TILE_ROW, t0 + q * Cfg::YBOX_TOK, dg0, g, b);
-            tma_store_commit();
-            if (tile + RT_STAGES < ntiles) issue(tile + RT_STAGES);   // stage s is free: every lane passed the syncwarp
-        }
+        __syncwarp();                                   // every lane is done with both stages
+        if (lane == 0) { mbar_arrive_s(empty + slot * 8); mbar_arrive_s(bcempty + bslot * 8); }
     }
-    if (lane == 0) tma_store_wait<0>();
     if (p.last && row_ok) {
 #pragma unroll
-        for (int n = 0; n < NST; ++n) p.last[((int64_t)b * p.dim + d) * NST + n] = h[n];
+        for (int i = 0; i < SPL; ++i) p.last[(b * p.dim + d) * NST + 2 * i + hf] = h[i];
     }
+}
+
+template <int NST, typename IN_T, bool HAS_Z>
+__device__ __forceinline__ void rows_producer(const ScanParams& p, uint8_t* base, int lane, int nvalid, int64_t b, int64_t g,
+                                              int64_t dg_cta, bool rev, const CUtensorMap* map_u, const CUtensorMap* map_d,
+                                              const CUtensorMap* map_z, const CUtensorMap* map_B, const CUtensorMap* map_C) {
+    using Cfg = RowsCfg<NST, IN_T, HAS_Z>;
+    constexpr int T = Cfg::T;
+    uint8_t* bcring = base + RT_NW * Cfg::RING;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bcring + RT_BCS * Cfg::BC);
+    const bool is_bc = lane == RT_NW;                    // lane RT_NW feeds the shared B/C ring, lanes < nvalid the warps
+    const bool mine = lane < nvalid || is_bc;
+    const int depth = is_bc ? RT_BCS : RT_STAGES;
+    uint64_t* full = is_bc ? bars + RT_NW * 2 * RT_STAGES : bars + (lane < RT_NW ? lane : 0) * 2 * RT_STAGES;
+    uint64_t* empty = full + depth;
+    uint8_t* ring = is_bc ? bcring : base + (lane < RT_NW ? lane : 0) * Cfg::RING;
+    const int stage_bytes = is_bc ? Cfg::BC : Cfg::ITEM;
+    const int ntiles = (int)((p.L + T - 1) / T);
+    const int total = mine ? ntiles : 0;
+    const int gu = (int)(g / p.u_gdiv), gi = (int)g, bi = (int)b;
+    const int dg0 = (int)dg_cta + (lane < RT_NW ? lane : 0) * RT_ROWS;
+    int tile = 0, slot = 0;
+    uint32_t fill = 0;
+    while (true) {
+        const bool active = tile < total;
+        if (!__any_sync(0xffffffffu, active)) break;
+        bool issued = false;
+        if (active && mbar_test_wait(&empty[slot], (fill - 1u) & 1u)) {
+            // mirrored walk for reversed groups: scan tile i covers memory tokens [L - (i+1)T, L - iT); a negative start is
+            // out of bounds for TMA and zero-filled, the consumer only touches the valid (high) end
+            const int t0 = rev ? (int)(p.L - (int64_t)(tile + 1) * T) : tile * T;
+            uint8_t* st = ring + slot * stage_bytes;
+            // TMA always delivers the whole box (out-of-bounds rows / tokens are zero-filled), so the byte count is fixed
+            mbar_arrive_expect_tx(&full[slot], (uint32_t)(is_bc ? 2 * NST * 128 : Cfg::ITEM));
+            if (is_bc) {
+                tma_load_4d(st, map_B, &full[slot], t0, 0, gi, bi);
+                tma_load_4d(st + Cfg::TB, map_C, &full[slot], t0, 0, gi, bi);
+            } else {
+                tma_load_4d(st, map_u, &full[slot], t0, dg0, gu, bi);
+                tma_load_4d(st + Cfg::TILE, map_d, &full[slot], t0, dg0, gi, bi);
+                if (HAS_Z) tma_load_4d(st + 2 * Cfg::TILE, map_z, &full[slot], t0, dg0, gi, bi);
+            }
+            if (++slot == depth) { slot = 0; ++fill; }
+            ++tile;
+            issued = true;
+        }
+        if (!__any_sync(0xffffffffu, issued)) __nanosleep(40);
+    }
+}
+
+template <int NST, typename IN_T, typename OUT_T, bool HAS_Z, bool SOFTPLUS>
+__global__ void __launch_bounds__((RT_NW + 1) * 32, 3)
+scan_rows_kernel(const ScanParams p, const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_d,
+                 const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_B,
+                 const __grid_constant__ CUtensorMap map_C) {
+    using Cfg = RowsCfg<NST, IN_T, HAS_Z>;
+    extern __shared__ uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t s0 = smem_u32(smem_raw);
+    const uint32_t pad = ((s0 + 1023u) & ~1023u) - s0;   // 1 KiB alignment: the 128B swizzle is a function of address bits 4..9
+    uint8_t* base = smem_raw + pad;
+
+    const int64_t Dg = p.dim / p.groups;
+    const int64_t rbpg = (Dg + RT_NW * RT_ROWS - 1) / (RT_NW * RT_ROWS);
+    const int64_t cta = blockIdx.x;
+    const int64_t rb = cta % rbpg, g = (cta / rbpg) % p.groups, b = cta / (rbpg * p.groups);
+    const int64_t dg_cta = rb * RT_NW * RT_ROWS;
+    const int nvalid = (int)min((int64_t)RT_NW, (Dg - dg_cta + RT_ROWS - 1) / RT_ROWS);
+    const bool rev = g < 64 && ((p.rev_mask >> g) & 1);
+    if (threadIdx.x == 0) {
+        uint64_t* bars = reinterpret_cast<uint64_t*>(base + RT_NW * Cfg::RING + RT_BCS * Cfg::BC);
+        for (int i = 0; i < RT_NW * 2 * RT_STAGES; ++i) mbar_init(&bars[i], 1);
+        for (int i = 0; i < RT_BCS; ++i) {
+            mbar_init(&bars[RT_NW * 2 * RT_STAGES + i], 1);                       // bcfull: the producer's expect_tx
+            mbar_init(&bars[RT_NW * 2 * RT_STAGES + RT_BCS + i], nvalid);          // bcempty: one arrival per live warp
+        }
+        fence_mbar_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+    if (warp == RT_NW) {
+        rows_producer<NST, IN_T, HAS_Z>(p, base, lane, nvalid, b, g, dg_cta, rev, &map_u, &map_d, &map_z, &map_B, &map_C);
+        return;
+    }
+    if (warp >= nvalid) return;
+    const uint32_t sbase = s0 + pad;
+    if (rev) rows_consumer<NST, IN_T, OUT_T, HAS_Z, SOFTPLUS, true>(p, sbase, warp, lane, b, g, dg_cta + warp * RT_ROWS);
+    else rows_consumer<NST, IN_T, OUT_T, HAS_Z, SOFTPLUS, false>(p, sbase, warp, lane, b, g, dg_cta + warp * RT_ROWS);
 }
 
 // ============================================================================================
@@ -676,49 +759,51 @@ template <int NST, typename IN_T, typename OUT_T> static int launch_lanes(ScanPa
     return launch_lanes_c<NST, IN_T, OUT_T, 8>(p, warps, st);
 }
 
-template <int NST, typename IN_T, typename OUT_T, bool HAS_Z>
-static int launch_rows_z(const ScanParams& p, int in_dt, int out_dt, cudaStream_t st) {
-    using Cfg = RowsCfg<NST, IN_T, OUT_T, HAS_Z>;
-    static_assert(Cfg::WARP_BYTES % 1024 == 0, "per-warp smem must keep 1024-B alignment for the 128B swizzle");
+template <int NST, typename IN_T, typename OUT_T, bool HAS_Z, bool SOFTPLUS>
+static int launch_rows_cfg(const ScanParams& p, int in_dt, cudaStream_t st) {
+    using Cfg = RowsCfg<NST, IN_T, HAS_Z>;
     const uint64_t Dg = (uint64_t)(p.dim / p.groups);
-    const uint64_t es = sizeof(IN_T), eo = sizeof(OUT_T);
-    CUtensorMap mu, md, mz, mB, mC, my;
+    const uint64_t es = sizeof(IN_T);
+    CUtensorMap mu, md, mz, mB, mC;
     {
-        const uint64_t dims[4] = {(uint64_t)p.L, Dg, (uint64_t)p.groups, (uint64_t)p.batch};
         const uint32_t box[4] = {(uint32_t)Cfg::T, RT_ROWS, 1, 1};
-        const uint64_t su[3] = {(uint64_t)p.u_ds * es, Dg * p.u_ds * es, (uint64_t)p.u_bs * es};
-        int rc = make_tensor_map(&mu, in_dt, 4, p.u, dims, su, box, 1);
+        const uint64_t udims[4] = {(uint64_t)p.L, Dg, (uint64_t)ceil_div(p.groups, p.u_gdiv), (uint64_t)p.batch};
+        const uint64_t su[3] = {(uint64_t)p.u_ds * es, (uint64_t)p.u_gs * es, (uint64_t)p.u_bs * es};
+        int rc = make_tensor_map(&mu, in_dt, 4, p.u, udims, su, box, 1);
         if (rc) return rc;
+        const uint64_t dims[4] = {(uint64_t)p.L, Dg, (uint64_t)p.groups, (uint64_t)p.batch};
         const uint64_t sd[3] = {(uint64_t)p.dl_ds * es, Dg * p.dl_ds * es, (uint64_t)p.dl_bs * es};
         if ((rc = make_tensor_map(&md, in_dt, 4, p.delta, dims, sd, box, 1))) return rc;
         if (HAS_Z) {
             const uint64_t sz[3] = {(uint64_t)p.z_ds * es, Dg * p.z_ds * es, (uint64_t)p.z_bs * es};
             if ((rc = make_tensor_map(&mz, in_dt, 4, p.z, dims, sz, box, 1))) return rc;
         } else {
-            mz = mu;
+            mz = md;
         }
-        const uint32_t ybox[4] = {(uint32_t)Cfg::YBOX_TOK, RT_ROWS, 1, 1};
-        const uint64_t so[3] = {(uint64_t)p.o_ds * eo, Dg * p.o_ds * eo, (uint64_t)p.o_bs * eo};
-        if ((rc = make_tensor_map(&my, out_dt, 4, p.out, dims, so, ybox, 1))) return rc;
         const uint64_t bdims[4] = {(uint64_t)p.L, (uint64_t)NST, (uint64_t)p.groups, (uint64_t)p.batch};
         const uint32_t bbox[4] = {(uint32_t)Cfg::T, NST, 1, 1};
         const uint64_t sB[3] = {(uint64_t)p.B_ss * es, (uint64_t)p.B_gs * es, (uint64_t)p.B_bs * es};
-        if ((rc = make_tensor_map(&mB, in_dt, 4, p.Bm, bdims, sB, bbox, 0))) return rc;
+        if ((rc = make_tensor_map(&mB, in_dt, 4, p.Bm, bdims, sB, bbox, 1))) return rc;
         const uint64_t sC[3] = {(uint64_t)p.C_ss * es, (uint64_t)p.C_gs * es, (uint64_t)p.C_bs * es};
-        if ((rc = make_tensor_map(&mC, in_dt, 4, p.Cm, bdims, sC, bbox, 0))) return rc;
+        if ((rc = make_tensor_map(&mC, in_dt, 4, p.Cm, bdims, sC, bbox, 1))) return rc;
     }
-    auto kern = scan_rows_tma_kernel<NST, IN_T, OUT_T, HAS_Z>;
+    auto kern = scan_rows_kernel<NST, IN_T, OUT_T, HAS_Z, SOFTPLUS>;
     XP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    const int64_t warps = p.batch * p.groups * ceil_div((int64_t)Dg, RT_ROWS);
-    kern<<<(unsigned)ceil_div(warps, RT_WARPS), RT_WARPS * 32, Cfg::SMEM, st>>>(p, mu, md, mz, mB, mC, my);
-    XP_LAUNCH_CHECK("scan_rows_tma_kernel");
+    const int64_t ctas = p.batch * p.groups * ceil_div((int64_t)Dg, RT_NW * RT_ROWS);
+    XP_REQUIRE(ctas < ((int64_t)1 << 31), "selective scan: too many row blocks for one launch");
+    kern<<<(unsigned)ctas, (RT_NW + 1) * 32, Cfg::SMEM, st>>>(p, mu, md, mz, mB, mC);
+    XP_LAUNCH_CHECK("scan_rows_kernel");
     return XP_OK;
 }
 
 template <int NST, typename IN_T, typename OUT_T>
-static int launch_rows(const ScanParams& p, int in_dt, int out_dt, cudaStream_t st) {
-    return p.z ? launch_rows_z<NST, IN_T, OUT_T, true>(p, in_dt, out_dt, st)
-               : launch_rows_z<NST, IN_T, OUT_T, false>(p, in_dt, out_dt, st);
+static int launch_rows(const ScanParams& p, int in_dt, cudaStream_t st) {
+    if (p.z) {
+        return p.softplus ? launch_rows_cfg<NST, IN_T, OUT_T, true, true>(p, in_dt, st)
+                          : launch_rows_cfg<NST, IN_T, OUT_T, true, false>(p, in_dt, st);
+    }
+    return p.softplus ? launch_rows_cfg<NST, IN_T, OUT_T, false, true>(p, in_dt, st)
+                      : launch_rows_cfg<NST, IN_T, OUT_T, false, false>(p, in_dt, st);
 }
 
 static bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; }
@@ -733,15 +818,14 @@ template <typename IN_T, typename OUT_T> static int dispatch(const ScanParams& p
                                   p.z ? p.z_bs : 0, p.z ? p.z_ds : 0};
     for (int64_t s : in_strides) vec_ok = vec_ok && (s % va == 0);
     vec_ok = vec_ok && (p.o_bs % vo == 0) && (p.o_ds % vo == 0);
-    const bool classic = p.rev_mask == 0 && p.u_gdiv == 1 && p.u_gs == (p.dim / p.groups) * p.u_ds;
     vec_ok = vec_ok && (p.u_gs % va == 0);
     if (vec_ok && p.dstate == 1) return launch_lanes<1, IN_T, OUT_T>(p, st);
     if (vec_ok && p.dstate == 2) return launch_lanes<2, IN_T, OUT_T>(p, st);
-    if (vec_ok && classic) {
+    if (vec_ok && p.L % 8 == 0 && p.batch < 32768 * 65536LL) {   // whole 8-token steps; TMA coordinates are int32
         switch (p.dstate) {
-            case 4: return launch_rows<4, IN_T, OUT_T>(p, a->in_dtype, a->out_dtype, st);
-            case 8: return launch_rows<8, IN_T, OUT_T>(p, a->in_dtype, a->out_dtype, st);
-            case 16: return launch_rows<16, IN_T, OUT_T>(p, a->in_dtype, a->out_dtype, st);
+            case 4: return launch_rows<4, IN_T, OUT_T>(p, a->in_dtype, st);
+            case 8: return launch_rows<8, IN_T, OUT_T>(p, a->in_dtype, st);
+            case 16: return launch_rows<16, IN_T, OUT_T>(p, a->in_dtype, st);
             default: break;
         }
     }

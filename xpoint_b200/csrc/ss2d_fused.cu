@@ -10,6 +10,8 @@
 //   * xp_ss2d_merge_norm:  y planes in NATURAL memory order [row-fwd, row-bwd, col-fwd, col-bwd] ->
 //                          LayerNorm_D(y0 + y1 + (y2 + y3)^T) [* gate] in channel-last layout, ONE pass:
 //                          16 B read + 2..4 B written per (token, channel), no intermediate buffer.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace xp {
@@ -52,19 +54,44 @@ __global__ void __launch_bounds__(256) ss2d_pack_kernel(const T* __restrict__ x,
 // ------------------------------------------------------------------------------------------ dwconv + SiLU + pack
 // in  : (B, H, W, *) channel-last, channel c of token (h, w) at in[((b*H + h)*W + w)*in_stride + c], c < D
 // out : xx (B, 2, D, L) = [act(conv(x)) ; its transpose]
-// One CTA: a TH x TW token tile (+1 halo) of CB channels.  Loads are channel-contiguous (the in_proj GEMM output
-// layout), stores are token-contiguous runs in both orders.
-constexpr int DW_TH = 16, DW_TW = 32, DW_CB = 16;
+// One CTA = 16 x 32 tokens (+1 halo) x 16 channels, 256 threads.
+//   load   : 16-byte vectors along the channels (the in_proj GEMM output layout) -> shared memory as channel PAIRS
+//   compute: thread = one channel pair x one row x 16 consecutive tokens; every input pair is read once per
+//            kernel row (54 LDS for 32 outputs) and the 3x3 weights live in registers
+//   store  : row-major plane straight from registers (32-byte runs); the column-major plane goes through a
+//            swizzled shared-memory transpose (aliasing the dead input tile) and leaves as 32-byte runs along h
+constexpr int DW_TH = 16, DW_TW = 32, DW_CB = 16, DW_NP = DW_CB / 2, DW_PITCH = DW_NP + 1;
+constexpr int DW_HT = DW_TH + 2, DW_WT = DW_TW + 2;
+
+template <typename T> struct DwPair;                      // two adjacent channels of one token in shared memory
+template <> struct DwPair<float> {
+    using type = float2;
+    static __device__ __forceinline__ float2 unpack(float2 v) { return v; }
+    static __device__ __forceinline__ float2 pack(float a, float b) { return make_float2(a, b); }
+};
+template <> struct DwPair<__half> {
+    using type = __half2;
+    static __device__ __forceinline__ float2 unpack(__half2 v) { return __half22float2(v); }
+    static __device__ __forceinline__ __half2 pack(float a, float b) { return __floats2half2_rn(a, b); }
+};
+template <> struct DwPair<__nv_bfloat16> {
+    using type = __nv_bfloat162;
+    static __device__ __forceinline__ float2 unpack(__nv_bfloat162 v) { return __bfloat1622float2(v); }
+    static __device__ __forceinline__ __nv_bfloat162 pack(float a, float b) { return __floats2bfloat162_rn(a, b); }
+};
 
 template <typename T, bool SILU>
 __global__ void __launch_bounds__(256) ss2d_dwconv_pack_kernel(const T* __restrict__ in, const float* __restrict__ wgt,
                                                                const float* __restrict__ bias, T* __restrict__ xx, int64_t D,
                                                                int H, int W, int64_t in_stride, int tiles_w, int tiles_h,
-                                                               int chan_blocks) {
-    constexpr int HT = DW_TH + 2, WT = DW_TW + 2;
-    __shared__ float sin[HT][WT][DW_CB + 1];
-    __shared__ float sw[DW_CB][9];
-    __shared__ float sb[DW_CB];
+                                                               int chan_blocks, int vec_in, int vec_row, int vec_col) {
+    using P = DwPair<T>;
+    using PairT = typename P::type;
+    constexpr int VEC = 16 / (int)sizeof(T);              // elements per 16-byte vector
+    constexpr int TILE_PAIRS = DW_HT * DW_WT * DW_PITCH;
+    constexpr int STAGE_ELEMS = DW_CB * DW_TW * DW_TH;
+    static_assert(STAGE_ELEMS * sizeof(T) <= TILE_PAIRS * sizeof(PairT), "transpose staging must fit in the input tile");
+    __shared__ __align__(16) PairT tile[TILE_PAIRS];
     const int64_t L = (int64_t)H * W;
     int64_t t = blockIdx.x;
     const int cb = (int)(t % chan_blocks); t /= chan_blocks;
@@ -73,60 +100,125 @@ __global__ void __launch_bounds__(256) ss2d_dwconv_pack_kernel(const T* __restri
     const int64_t b = t;
     const int h0 = th * DW_TH, w0 = tw * DW_TW, c0 = cb * DW_CB;
     const int tid = threadIdx.x;
-    if (tid < DW_CB * 9) {
-        const int c = tid / 9, k = tid % 9;
-        sw[c][k] = c0 + c < D ? wgt[(int64_t)(c0 + c) * 9 + k] : 0.0f;
+
+    // ---- load the halo tile
+    const T* inb = in + b * H * (int64_t)W * in_stride;
+    if (vec_in) {                                         // D % VEC == 0: vectors are all-or-nothing against D
+        constexpr int VPT = DW_CB / VEC;                  // vectors per token
+        for (int i = tid; i < DW_HT * DW_WT * VPT; i += 256) {
+            const int v = i % VPT, tok = i / VPT;
+            const int hh = tok / DW_WT, ww = tok % DW_WT;
+            const int h = h0 + hh - 1, w = w0 + ww - 1;
+            uint4 raw = make_uint4(0u, 0u, 0u, 0u);       // zero padding (Conv2d padding=1)
+            if (h >= 0 && h < H && w >= 0 && w < W && c0 + v * VEC < D)
+                raw = __ldg(reinterpret_cast<const uint4*>(inb + ((int64_t)h * W + w) * in_stride + c0 + v * VEC));
+            const PairT* pr = reinterpret_cast<const PairT*>(&raw);
+#pragma unroll
+            for (int j = 0; j < VEC / 2; ++j) tile[tok * DW_PITCH + v * (VEC / 2) + j] = pr[j];
+        }
+    } else {
+        for (int i = tid; i < DW_HT * DW_WT * DW_NP; i += 256) {
+            const int pr = i % DW_NP, tok = i / DW_NP;
+            const int hh = tok / DW_WT, ww = tok % DW_WT;
+            const int h = h0 + hh - 1, w = w0 + ww - 1;
+            float a = 0.0f, c = 0.0f;
+            if (h >= 0 && h < H && w >= 0 && w < W) {
+                const T* src = inb + ((int64_t)h * W + w) * in_stride + c0 + 2 * pr;
+                if (c0 + 2 * pr < D) a = to_f32(src[0]);
+                if (c0 + 2 * pr + 1 < D) c = to_f32(src[1]);
+            }
+            tile[tok * DW_PITCH + pr] = P::pack(a, c);
+        }
     }
-    if (tid < DW_CB) sb[tid] = (bias && c0 + tid < D) ? bias[c0 + tid] : 0.0f;
-    // load the halo tile: consecutive threads -> consecutive channels of one token
-    for (int i = tid; i < HT * WT * DW_CB; i += 256) {
-        const int c = i % DW_CB, tok = i / DW_CB;
-        const int hh = tok / WT, ww = tok % WT;
-        const int h = h0 + hh - 1, w = w0 + ww - 1;
-        float v = 0.0f;                                              // zero padding (Conv2d padding=1)
-        if (h >= 0 && h < H && w >= 0 && w < W && c0 + c < D) v = to_f32(in[((b * H + h) * (int64_t)W + w) * in_stride + c0 + c]);
-        sin[hh][ww][c] = v;
+    // ---- this thread's pair / row / strip, weights in registers
+    const int hh = tid % DW_TH, pr = (tid / DW_TH) % DW_NP, strip = tid / (DW_TH * DW_NP);   // strip: 16 tokens
+    const int cA = c0 + 2 * pr, cB = cA + 1;
+    float wa[9], wb[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        wa[k] = cA < D ? __ldg(wgt + (int64_t)cA * 9 + k) : 0.0f;
+        wb[k] = cB < D ? __ldg(wgt + (int64_t)cB * 9 + k) : 0.0f;
+    }
+    const float ba = (bias && cA < D) ? __ldg(bias + cA) : 0.0f, bb = (bias && cB < D) ? __ldg(bias + cB) : 0.0f;
+    __syncthreads();
+    constexpr int NT = 16;
+    float ya[NT], yb[NT];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) { ya[j] = ba; yb[j] = bb; }
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const PairT* row = tile + ((hh + ky) * DW_WT + strip * NT) * DW_PITCH + pr;
+#pragma unroll
+        for (int q = 0; q < NT + 2; ++q) {
+            const float2 v = P::unpack(row[q * DW_PITCH]);
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int j = q - kx;
+                if (j >= 0 && j < NT) {
+                    ya[j] = fmaf(v.x, wa[ky * 3 + kx], ya[j]);
+                    yb[j] = fmaf(v.y, wb[ky * 3 + kx], yb[j]);
+                }
+            }
+        }
+    }
+    if (SILU) {
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            ya[j] = ya[j] / (1.0f + __expf(-ya[j]));
+            yb[j] = yb[j] / (1.0f + __expf(-yb[j]));
+        }
+    }
+    // ---- row-major plane: 16 consecutive tokens per channel straight from registers
+    const int h = h0 + hh, wbeg = w0 + strip * NT;
+    if (h < H) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int c = e ? cB : cA;
+            if (c >= D) continue;
+            const float* y = e ? yb : ya;
+            T* dst = xx + ((b * 2 + 0) * D + c) * L + (int64_t)h * W + wbeg;
+            if (vec_row) {                                 // W % VEC == 0: vectors are all-or-nothing against W
+#pragma unroll
+                for (int v = 0; v < NT / VEC; ++v) {
+                    if (wbeg + v * VEC >= W) break;
+                    uint4 raw;
+                    T* o = reinterpret_cast<T*>(&raw);
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) o[j] = from_f32<T>(y[v * VEC + j]);
+                    *reinterpret_cast<uint4*>(dst + v * VEC) = raw;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < NT; ++j)
+                    if (wbeg + j < W) dst[j] = from_f32<T>(y[j]);
+            }
+        }
+    }
+    // ---- column-major plane: transpose through shared memory, layout [c][w'][h] with w' = (w + c/2) & 31 so that a
+    //      warp (16 rows x 2 pairs) writes 16 different banks, two rows per 32-bit word
+    __syncthreads();                                      // every thread is done reading the input tile
+    T* stage = reinterpret_cast<T*>(tile);
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+        const int wsw = (strip * NT + j + pr) & (DW_TW - 1);
+        stage[((2 * pr) * DW_TW + wsw) * DW_TH + hh] = from_f32<T>(ya[j]);
+        stage[((2 * pr + 1) * DW_TW + wsw) * DW_TH + hh] = from_f32<T>(yb[j]);
     }
     __syncthreads();
-    // compute into registers (thread -> channel tid % CB, tokens tid / CB + 16 k), then park the results in the same
-    // shared memory (the halo tile is dead by then) for the token-contiguous stores
-    constexpr int PER = DW_CB * DW_TH * DW_TW / 256;
-    float acc[PER];
+    constexpr int VPC = DW_TH / VEC;                       // vectors per (channel, column)
+    for (int i = tid; i < DW_CB * DW_TW * VPC; i += 256) {
+        const int v = i % VPC, ww = (i / VPC) % DW_TW, cl = i / (VPC * DW_TW);
+        const int c = c0 + cl, w = w0 + ww, hb = h0 + v * VEC;
+        if (c >= D || w >= W || hb >= H) continue;
+        const T* src = stage + (cl * DW_TW + ((ww + cl / 2) & (DW_TW - 1))) * DW_TH + v * VEC;
+        T* dst = xx + ((b * 2 + 1) * D + c) * L + (int64_t)w * H + hb;
+        if (vec_col) {                                     // H % VEC == 0
+            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+        } else {
 #pragma unroll
-    for (int k = 0; k < PER; ++k) {
-        const int i = tid + 256 * k;
-        const int c = i % DW_CB, tok = i / DW_CB;
-        const int hh = tok / DW_TW, ww = tok % DW_TW;
-        float a = sb[c];
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) a = fmaf(sin[hh + ky][ww + kx][c], sw[c][ky * 3 + kx], a);
-        if (SILU) a = a / (1.0f + __expf(-a));
-        acc[k] = a;
-    }
-    __syncthreads();
-    constexpr int CP = DW_TH * (DW_TW + 1) + 1;            // odd channel pitch: conflict-free channel-fastest writes
-    static_assert(DW_CB * CP <= HT * WT * (DW_CB + 1), "output staging must fit in the halo tile");
-    float* sout = &sin[0][0][0];
-#pragma unroll
-    for (int k = 0; k < PER; ++k) {
-        const int i = tid + 256 * k;
-        const int c = i % DW_CB, tok = i / DW_CB;
-        sout[c * CP + (tok / DW_TW) * (DW_TW + 1) + tok % DW_TW] = acc[k];
-    }
-    __syncthreads();
-    // row-major plane: runs of DW_TW tokens
-    for (int i = tid; i < DW_CB * DW_TH * DW_TW; i += 256) {
-        const int ww = i % DW_TW, hh = (i / DW_TW) % DW_TH, c = i / (DW_TW * DW_TH);
-        const int h = h0 + hh, w = w0 + ww;
-        if (h < H && w < W && c0 + c < D) xx[((b * 2 + 0) * D + c0 + c) * L + (int64_t)h * W + w] = from_f32<T>(sout[c * CP + hh * (DW_TW + 1) + ww]);
-    }
-    // column-major plane: runs of DW_TH tokens
-    for (int i = tid; i < DW_CB * DW_TH * DW_TW; i += 256) {
-        const int hh = i % DW_TH, ww = (i / DW_TH) % DW_TW, c = i / (DW_TW * DW_TH);
-        const int h = h0 + hh, w = w0 + ww;
-        if (h < H && w < W && c0 + c < D) xx[((b * 2 + 1) * D + c0 + c) * L + (int64_t)w * H + h] = from_f32<T>(sout[c * CP + hh * (DW_TW + 1) + ww]);
+            for (int j = 0; j < VEC; ++j)
+                if (hb + j < H) dst[j] = src[j];
+        }
     }
 }
 
@@ -134,86 +226,150 @@ __global__ void __launch_bounds__(256) ss2d_dwconv_pack_kernel(const T* __restri
 // CTA = TH x TW token tile, all D channels, fp32 tile[token][D | 1] in shared memory.
 //   phase 1: tile  = y0 + y1        row-major planes, float4 = 4 consecutive w
 //   phase 2: tile += y2 + y3        column-major planes, float4 = 4 consecutive h
-//   phase 3: warp per token: two-pass LayerNorm over the D channels, affine, optional gate, channel-last store
-template <typename TO, int TH, int TW>
+//   phase 3: warp per token: two-pass LayerNorm over the D channels (row held in registers when DPER > 0),
+//            affine, optional gate, channel-last store
+template <typename TO, int TH, int TW, int DPER>
 __global__ void __launch_bounds__(256) ss2d_merge_norm_kernel(const float* __restrict__ ys, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, const TO* __restrict__ zact,
                                                               TO* __restrict__ out, int D, int H, int W, int tiles_w,
                                                               int tiles_h, float eps) {
     extern __shared__ __align__(16) float tile[];
     const int P = D | 1;                                   // odd pitch: conflict-free token-major writes
-    const int64_t L = (int64_t)H * W;
+    const int L = H * W;                                   // D * L < 2^31 (host-checked): 32-bit offsets inside a plane set
     int64_t t = blockIdx.x;
     const int tw = (int)(t % tiles_w); t /= tiles_w;
     const int th = (int)(t % tiles_h); t /= tiles_h;
     const int64_t b = t;
     const int h0 = th * TH, w0 = tw * TW;
     const int tid = threadIdx.x;
-    const float* y0 = ys + (b * 4 + 0) * D * L;
-    const float* y1 = ys + (b * 4 + 1) * D * L;
-    const float* y2 = ys + (b * 4 + 2) * D * L;
-    const float* y3 = ys + (b * 4 + 3) * D * L;
+    const float* y0 = ys + (b * 4 + 0) * D * (int64_t)L;
+    const float* y1 = y0 + (int64_t)D * L;
+    const float* y2 = y1 + (int64_t)D * L;
+    const float* y3 = y2 + (int64_t)D * L;
     constexpr int QW = TW / 4, QH = TH / 4;
     // phase 1
-    for (int i = tid; i < D * TH * QW; i += 256) {
-        const int q = i % QW, hh = (i / QW) % TH, c = i / (QW * TH);
+    {
+        const int q = tid % QW, hh = (tid / QW) % TH, cstep = 256 / (QW * TH);
         const int h = h0 + hh, w = w0 + 4 * q;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (h < H && w < W) {                               // W % 4 == 0: quads are all-or-nothing
-            const int64_t o = (int64_t)c * L + (int64_t)h * W + w;
-            const float4 a = __ldg(reinterpret_cast<const float4*>(y0 + o));
-            const float4 r = __ldg(reinterpret_cast<const float4*>(y1 + o));
-            v = make_float4(a.x + r.x, a.y + r.y, a.z + r.z, a.w + r.w);
+        const bool ok = h < H && w < W;                    // W % 4 == 0: quads are all-or-nothing
+        const int base = h * W + w;
+        float* dst = tile + (hh * TW + 4 * q) * P;
+#pragma unroll 4
+        for (int c = tid / (QW * TH); c < D; c += cstep) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(y0 + c * L + base));
+                const float4 r = __ldg(reinterpret_cast<const float4*>(y1 + c * L + base));
+                v = make_float4(a.x + r.x, a.y + r.y, a.z + r.z, a.w + r.w);
+            }
+            dst[c] = v.x; dst[P + c] = v.y; dst[2 * P + c] = v.z; dst[3 * P + c] = v.w;
         }
-        float* dst = tile + (hh * TW + 4 * q) * P + c;
-        dst[0] = v.x; dst[P] = v.y; dst[2 * P] = v.z; dst[3 * P] = v.w;
     }
     __syncthreads();
     // phase 2
-    for (int i = tid; i < D * TW * QH; i += 256) {
-        const int q = i % QH, ww = (i / QH) % TW, c = i / (QH * TW);
+    {
+        const int q = tid % QH, ww = (tid / QH) % TW, cstep = 256 / (QH * TW);
         const int w = w0 + ww, h = h0 + 4 * q;
-        if (h < H && w < W) {
-            const int64_t o = (int64_t)c * L + (int64_t)w * H + h;
-            const float4 a = __ldg(reinterpret_cast<const float4*>(y2 + o));
-            const float4 r = __ldg(reinterpret_cast<const float4*>(y3 + o));
-            float* dst = tile + ((4 * q) * TW + ww) * P + c;
-            dst[0] += a.x + r.x; dst[TW * P] += a.y + r.y; dst[2 * TW * P] += a.z + r.z; dst[3 * TW * P] += a.w + r.w;
+        const bool ok = h < H && w < W;
+        const int base = w * H + h;
+        float* dst = tile + ((4 * q) * TW + ww) * P;
+        if (ok) {
+#pragma unroll 4
+            for (int c = tid / (QH * TW); c < D; c += cstep) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(y2 + c * L + base));
+                const float4 r = __ldg(reinterpret_cast<const float4*>(y3 + c * L + base));
+                dst[c] += a.x + r.x; dst[TW * P + c] += a.y + r.y; dst[2 * TW * P + c] += a.z + r.z;
+                dst[3 * TW * P + c] += a.w + r.w;
+            }
         }
     }
     __syncthreads();
     // phase 3
     const int warp = tid >> 5, lane = tid & 31;
-    for (int tok = warp; tok < TH * TW; tok += 8) {
-        const int h = h0 + tok / TW, w = w0 + tok % TW;
-        if (h >= H || w >= W) continue;                     // warp-uniform
-        const float* row = tile + tok * P;
-        float s = 0.0f;
-        for (int c = lane; c < D; c += 32) s += row[c];
-        const float mean = warp_sum(s) / (float)D;
-        float ss = 0.0f;
-        for (int c = lane; c < D; c += 32) { const float dlt = row[c] - mean; ss += dlt * dlt; }
-        const float rstd = rsqrtf(warp_sum(ss) / (float)D + eps);
-        const int64_t o = (b * L + (int64_t)h * W + w) * D;
-        for (int c = lane; c < D; c += 32) {
-            float v = (row[c] - mean) * rstd * gamma[c] + beta[c];
-            if (zact) v *= to_f32(zact[o + c]);
-            out[o + c] = from_f32<TO>(v);
+    if constexpr (DPER > 0) {
+        float gm[DPER], bt[DPER];
+#pragma unroll
+        for (int i = 0; i < DPER; ++i) {
+            const int c = lane + 32 * i;
+            gm[i] = c < D ? __ldg(gamma + c) : 0.0f;
+            bt[i] = c < D ? __ldg(beta + c) : 0.0f;
+        }
+        const float invD = 1.0f / (float)D;
+        for (int tok = warp; tok < TH * TW; tok += 8) {
+            const int h = h0 + tok / TW, w = w0 + tok % TW;
+            if (h >= H || w >= W) continue;                // warp-uniform
+            const float* row = tile + tok * P;
+            float v[DPER];
+            float s = 0.0f;
+#pragma unroll
+            for (int i = 0; i < DPER; ++i) {
+                const int c = lane + 32 * i;
+                v[i] = c < D ? row[c] : 0.0f;
+                s += v[i];
+            }
+            const float mean = warp_sum(s) * invD;
+            float ss = 0.0f;
+#pragma unroll
+            for (int i = 0; i < DPER; ++i) {
+                const float dlt = (lane + 32 * i < D) ? v[i] - mean : 0.0f;
+                v[i] = dlt;
+                ss = fmaf(dlt, dlt, ss);
+            }
+            const float rstd = rsqrtf(warp_sum(ss) * invD + eps);
+            const int64_t o = (b * L + (int64_t)h * W + w) * D;
+#pragma unroll
+            for (int i = 0; i < DPER; ++i) {
+                const int c = lane + 32 * i;
+                if (c < D) {
+                    float r = fmaf(v[i] * rstd, gm[i], bt[i]);
+                    if (zact) r *= to_f32(zact[o + c]);
+                    out[o + c] = from_f32<TO>(r);
+                }
+            }
+        }
+    } else {
+        for (int tok = warp; tok < TH * TW; tok += 8) {
+            const int h = h0 + tok / TW, w = w0 + tok % TW;
+            if (h >= H || w >= W) continue;                // warp-uniform
+            const float* row = tile + tok * P;
+            float s = 0.0f;
+            for (int c = lane; c < D; c += 32) s += row[c];
+            const float mean = warp_sum(s) / (float)D;
+            float ss = 0.0f;
+            for (int c = lane; c < D; c += 32) { const float dlt = row[c] - mean; ss += dlt * dlt; }
+            const float rstd = rsqrtf(warp_sum(ss) / (float)D + eps);
+            const int64_t o = (b * L + (int64_t)h * W + w) * D;
+            for (int c = lane; c < D; c += 32) {
+                float v = (row[c] - mean) * rstd * gamma[c] + beta[c];
+                if (zact) v *= to_f32(zact[o + c]);
+                out[o + c] = from_f32<TO>(v);
+            }
         }
     }
 }
 
-template <typename TO, int TH, int TW>
-static int merge_norm_launch(const float* ys, const float* gamma, const float* beta, const void* zact, void* out, int64_t B,
-                             int64_t D, int64_t H, int64_t W, float eps, cudaStream_t st) {
+template <typename TO, int TH, int TW, int DPER>
+static int merge_norm_launch_d(const float* ys, const float* gamma, const float* beta, const void* zact, void* out, int64_t B,
+                               int64_t D, int64_t H, int64_t W, float eps, cudaStream_t st) {
     const int tiles_w = (int)ceil_div(W, TW), tiles_h = (int)ceil_div(H, TH);
     const int smem = TH * TW * (int)(D | 1) * 4;
-    auto kern = ss2d_merge_norm_kernel<TO, TH, TW>;
+    auto kern = ss2d_merge_norm_kernel<TO, TH, TW, DPER>;
     XP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kern<<<(unsigned)(B * tiles_h * tiles_w), 256, smem, st>>>(ys, gamma, beta, (const TO*)zact, (TO*)out, (int)D, (int)H, (int)W,
                                                                  tiles_w, tiles_h, eps);
     XP_LAUNCH_CHECK("ss2d_merge_norm_kernel");
     return XP_OK;
+}
+
+template <typename TO, int TH, int TW>
+static int merge_norm_launch(const float* ys, const float* gamma, const float* beta, const void* zact, void* out, int64_t B,
+                             int64_t D, int64_t H, int64_t W, float eps, cudaStream_t st) {
+    const int per = (int)ceil_div(D, 32);                  // channels per lane in the LayerNorm phase
+    if (per <= 3) return merge_norm_launch_d<TO, TH, TW, 3>(ys, gamma, beta, zact, out, B, D, H, W, eps, st);
+    if (per <= 6) return merge_norm_launch_d<TO, TH, TW, 6>(ys, gamma, beta, zact, out, B, D, H, W, eps, st);
+    if (per <= 12) return merge_norm_launch_d<TO, TH, TW, 12>(ys, gamma, beta, zact, out, B, D, H, W, eps, st);
+    if (per <= 24) return merge_norm_launch_d<TO, TH, TW, 24>(ys, gamma, beta, zact, out, B, D, H, W, eps, st);
+    return merge_norm_launch_d<TO, TH, TW, 0>(ys, gamma, beta, zact, out, B, D, H, W, eps, st);
 }
 
 template <typename TO>
@@ -256,8 +412,13 @@ extern "C" int xp_ss2d_dwconv_pack(const void* in, const float* weight, const fl
     const int64_t grid = B * tiles_w * tiles_h * cbs;
     XP_REQUIRE(grid < (int64_t)1 << 31, "xp_ss2d_dwconv_pack: problem too large for one launch");
     cudaStream_t st = (cudaStream_t)stream;
+    const int64_t vec = dtype == XP_F32 ? 4 : 8;           // elements per 16-byte vector
+    const bool al_in = (reinterpret_cast<uintptr_t>(in) & 15) == 0, al_out = (reinterpret_cast<uintptr_t>(xx) & 15) == 0;
+    const int vec_in = al_in && in_token_stride % vec == 0 && D % vec == 0;
+    const int vec_row = al_out && W % vec == 0, vec_col = al_out && H % vec == 0 && (H * W) % vec == 0;
 #define XP_DW(T, S) ss2d_dwconv_pack_kernel<T, S><<<(unsigned)grid, 256, 0, st>>>((const T*)in, weight, bias, (T*)xx, D, (int)H, \
-                                                                                   (int)W, in_token_stride, tiles_w, tiles_h, cbs)
+                                                                                   (int)W, in_token_stride, tiles_w, tiles_h, cbs, \
+                                                                                   vec_in, vec_row, vec_col)
     if (dtype == XP_F32) { if (silu) XP_DW(float, true); else XP_DW(float, false); }
     else if (dtype == XP_F16) { if (silu) XP_DW(__half, true); else XP_DW(__half, false); }
     else { if (silu) XP_DW(__nv_bfloat16, true); else XP_DW(__nv_bfloat16, false); }
@@ -274,6 +435,7 @@ extern "C" int xp_ss2d_merge_norm(const float* ys, const float* gamma, const flo
     XP_REQUIRE(H % 4 == 0 && W % 4 == 0, "xp_ss2d_merge_norm: H and W must be multiples of 4 (got %lld x %lld)", (long long)H,
                (long long)W);
     XP_REQUIRE(D <= 3072, "xp_ss2d_merge_norm: D must be <= 3072 (got %lld)", (long long)D);
+    XP_REQUIRE(D * H * W < ((int64_t)1 << 31), "xp_ss2d_merge_norm: D*H*W must be < 2^31");
     XP_REQUIRE(out_dtype >= XP_F32 && out_dtype <= XP_BF16, "xp_ss2d_merge_norm: unsupported dtype %d", out_dtype);
     XP_REQUIRE((reinterpret_cast<uintptr_t>(ys) & 15) == 0, "xp_ss2d_merge_norm: ys must be 16-byte aligned");
     if (B == 0) return XP_OK;

@@ -142,6 +142,20 @@ __device__ __forceinline__ float lg2_approx(float x) {
     return y;
 }
 
+// Packed FP32 pairs (Blackwell FFMA2 / FMUL2: two IEEE fp32 operations per issue slot, same rounding as the scalar ops)
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
+        "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
+        "l"(*reinterpret_cast<unsigned long long*>(&b)), "l"(*reinterpret_cast<unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&r);
+}
+
 // softplus(beta=1, threshold=20) as torch / the reference kernel define it (csms6s.py:49-50,
 // selective_scan_fwd_kernel_oflex.cuh:124-127): x > 20 ? x : log1p(exp(x)).  Branch-free, 2 MUFU + ~10 FP32 ops
 // (libdevice log1pf costs ~35 instructions and two branches):  e = exp(x);

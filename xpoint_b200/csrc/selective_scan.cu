@@ -542,33 +542,40 @@ __device__ __forceinline__ void rows_consumer(const ScanParams& p, uint32_t sbas
             float u8[8], d8[8];
             lds_group8<IN_T, REV>(su, r, c8, u8);
             lds_group8<IN_T, REV>(sd, r, c8, d8);
-            // this lane evaluates tokens 2j + hf, then the pair swaps: 4 softplus per lane instead of 8
-            float dl[8], du[8], yp[8];
+            // this lane evaluates tokens 2j + hf, then the pair swaps: 4 softplus per lane instead of 8.
+            // Token pairs (2j, 2j+1) stay packed as float2 so the per-state multiplies and the y update issue as
+            // FMUL2 / FFMA2 (two fp32 ops per issue slot); only the recurrence itself is scalar.
+            float2 dl2[4], du2[4], yp2[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float uo = hf ? u8[2 * j + 1] : u8[2 * j];
                 const float x = (hf ? d8[2 * j + 1] : d8[2 * j]) + bias;
                 const float dlo = SOFTPLUS ? softplus_f(x) : x;
                 const float duo = dlo * uo;
-                dl[2 * j] = __shfl_sync(0xffffffffu, dlo, src0);
-                dl[2 * j + 1] = __shfl_sync(0xffffffffu, dlo, src1);
-                du[2 * j] = __shfl_sync(0xffffffffu, duo, src0);
-                du[2 * j + 1] = __shfl_sync(0xffffffffu, duo, src1);
-                yp[2 * j] = Dm0 * uo;
-                yp[2 * j + 1] = Dm1 * uo;
+                dl2[j] = make_float2(__shfl_sync(0xffffffffu, dlo, src0), __shfl_sync(0xffffffffu, dlo, src1));
+                du2[j] = make_float2(__shfl_sync(0xffffffffu, duo, src0), __shfl_sync(0xffffffffu, duo, src1));
+                yp2[j] = make_float2(Dm0 * uo, Dm1 * uo);
             }
 #pragma unroll
             for (int i = 0; i < SPL; ++i) {
                 float bv[8], cv[8];
                 lds_group8<IN_T, REV>(sB, 2 * i + hf, c8, bv);
                 lds_group8<IN_T, REV>(sC, 2 * i + hf, c8, cv);
+                const float2 A2d = make_float2(A2[i], A2[i]);
 #pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    const float a = ex2_approx(dl[t] * A2[i]);
-                    h[i] = fmaf(a, h[i], du[t] * bv[t]);
-                    yp[t] = fmaf(h[i], cv[t], yp[t]);
+                for (int q = 0; q < 4; ++q) {
+                    const float2 arg = mul2(dl2[q], A2d);
+                    const float2 xb = mul2(du2[q], make_float2(bv[2 * q], bv[2 * q + 1]));
+                    float2 hh;
+                    hh.x = fmaf(ex2_approx(arg.x), h[i], xb.x);
+                    hh.y = fmaf(ex2_approx(arg.y), hh.x, xb.y);
+                    h[i] = hh.y;
+                    yp2[q] = fma2(hh, make_float2(cv[2 * q], cv[2 * q + 1]), yp2[q]);
                 }
             }
+            float yp[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { yp[2 * q] = yp2[q].x; yp[2 * q + 1] = yp2[q].y; }
             const int64_t tok = (int64_t)tile * T + c8 * 8;          // first scan-order token of the group
             if constexpr (sizeof(OUT_T) == 4) {
                 // lane hf finishes tokens 4*hf .. 4*hf+3: send the partner's half, keep mine

@@ -140,3 +140,32 @@ def test_pipeline_tail_vs_oracle():
         if gap.min() > 1e-5:
             assert got == list(zip(q.tolist(), t.tolist()))
         assert int(r.n_matches[b]) == len(got)
+
+
+def test_config5_highres_pair_runs_and_agrees():
+    """BASELINE configs[4]: one 1024x1280 pair (stage-0 scan length 81 920), preset E, top-16384 keypoints.  fp16 autocast
+    on the copy-free path against fp32 on the CrossScan/CrossMerge path; the tail must return full keypoint sets."""
+    import xpoint_b200 as X
+    torch.manual_seed(0)
+    g = torch.Generator().manual_seed(0)
+    o = torch.rand(1, 1, 1024, 1280, generator=g).to(DEV)
+    t = torch.rand(1, 1, 1024, 1280, generator=g).to(DEV)
+    outs = {}
+    for mixed in (False, True):
+        torch.manual_seed(0)
+        net = X.XPoint({"takes_pair": True, "mixed_precision": mixed, "use_attention": {"preset": "E"}}).to(DEV).eval()
+        for m in net.modules():
+            if isinstance(m, X.SS2D):
+                m.disable_fused = not mixed
+        with torch.no_grad():
+            po, pt = net.forward_pair_batched(o, t)
+        outs[mixed] = po
+        if mixed:
+            pipe = X.PairPipeline(net, keep_top_k=16384)
+            r = pipe(o, t)
+            assert r.kp_optical.shape == (1, 16384, 2) and 0 < int(r.n_optical[0]) <= 16384
+            assert 0 <= int(r.n_matches[0]) <= int(r.n_optical[0])
+    for k in ("encoder_output", "prob", "desc"):
+        assert outs[True][k].shape == outs[False][k].shape
+        assert_close(outs[True][k].float().cpu().numpy(), outs[False][k].float().cpu().numpy(), 1e-2, "config 5 " + k)
+    assert outs[True]["prob"].shape == (1, 1, 1024, 1280) and outs[True]["desc"].shape == (1, 256, 128, 160)

@@ -184,3 +184,31 @@ def test_match_batched_ragged_and_ties(tc):
     b = torch.stack([base[0], base[1], base[1]])
     m = X.get_matches(a.to(DEV), b.to(DEV), "bfmatcher", crossCheck=True, use_tensor_cores=tc)
     assert _pairs(m) == [(0, 0), (2, 1)]
+
+
+def test_match_config5_size_16384():
+    """BASELINE configs[4]: 16 384 keypoints per image (1024x1280 pairs) -> a 16 384^2 x 256 similarity GEMM.  The float64
+    oracle is too slow for the whole matrix, so: tcgen05 path == exact-fp32 CUDA-core path everywhere, and 512 sampled
+    query rows == float64 numpy arg-min (size-independent property)."""
+    X, _ = _imports()
+    n = 16384
+    d1, d2 = _descs(n, n, 5)
+    a, b = d1[None].to(DEV), d2[None].to(DEV)
+    r_tc = X.mnn_match(a, b, use_tensor_cores=True)
+    r_fp = X.mnn_match(a, b, use_tensor_cores=False)
+    nn_tc, nn_fp = r_tc.nn12[0].cpu().numpy(), r_fp.nn12[0].cpu().numpy()
+    rows = np.random.default_rng(0).choice(n, 512, replace=False)
+    dist = ((d1.numpy()[rows, None, :].astype(np.float64) - d2.numpy()[None, :, :].astype(np.float64)) ** 2).sum(-1)
+    order = np.sort(dist, axis=1)
+    clear = (order[:, 1] - order[:, 0]) > 1e-5                     # min-gap guard (SURVEY C.13)
+    assert clear.mean() > 0.99
+    assert np.array_equal(nn_tc[rows][clear], dist.argmin(1)[clear])
+    assert np.array_equal(nn_fp[rows][clear], dist.argmin(1)[clear])
+    assert (nn_tc != nn_fp).mean() < 1e-3                          # only fp32-noise ties may differ
+    m_tc, m_fp = r_tc.match_idx[0].cpu().numpy(), r_fp.match_idx[0].cpu().numpy()
+    assert (m_tc != m_fp).mean() < 2e-3
+    assert abs(int(r_tc.count[0]) - int(r_fp.count[0])) <= 0.002 * n
+    # mutual consistency of the returned pairs
+    nn21 = r_tc.nn21[0].cpu().numpy()
+    q = np.nonzero(m_tc >= 0)[0]
+    assert np.array_equal(nn21[m_tc[q]], q)

@@ -47,7 +47,7 @@ class LayerNorm(nn.LayerNorm):
     def forward(self, x):
         out_dtype = None
         if torch.is_autocast_enabled():
-            out_dtype = torch.get_autocast_gpu_dtype() if self.for_matmul else torch.float32
+            out_dtype = torch.get_autocast_dtype('cuda') if self.for_matmul else torch.float32
         return layer_norm(x, self.weight, self.bias, self.eps, out_dtype)
 
 

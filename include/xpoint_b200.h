@@ -168,6 +168,22 @@ XP_API int xp_ss2d_merge_norm(const float* ys, const float* gamma, const float* 
 XP_API int xp_layer_norm(const void* x, const float* gamma, const float* beta, void* y, int64_t rows, int64_t C,
                          int32_t in_dtype, int32_t out_dtype, float eps, xp_stream_t stream);
 
+/* -- f2: residual add + bias + LayerNorm in one pass; patch-embed stem -----------------------
+ * xp_add_layer_norm replaces `x = x + branch; n = LayerNorm(x)` of VSSBlock (VMamba.py:1222-1234) and the
+ * `conv bias -> permute -> LayerNorm` tails of patch-embed / downsample (VMamba.py:1405-1440):
+ *     s = x [+ res] [+ pre_bias] ;  sum_out = s (optional) ;  y = LayerNorm_C(s) * gamma + beta (optional)
+ * x, res, y, sum_out: (rows, C) channel-last, each with its own dtype; pre_bias / gamma / beta: (C) fp32.  C <= 1536.
+ * xp_patch_embed_stem replaces cat(x,x,x) -> Conv2d(3 -> C1, k3, s2, p1) -> permute -> LayerNorm(C1) -> permute -> GELU
+ * (VMamba.py:1405-1413, :1509-1510): img (B, Cin, H, W) fp32 with Cin 1 (weights pre-summed over the replicated
+ * channels by the caller) or 3, weight (C1, Cin, 3, 3) fp32 -> out (B, ceil(H/2), ceil(W/2), C1) channel-last.
+ */
+XP_API int xp_add_layer_norm(const void* x, const void* res, const float* pre_bias, const float* gamma, const float* beta,
+                             void* y, void* sum_out, int64_t rows, int64_t C, int32_t x_dtype, int32_t res_dtype,
+                             int32_t y_dtype, int32_t sum_dtype, float eps, xp_stream_t stream);
+XP_API int xp_patch_embed_stem(const float* img, const float* weight, const float* bias, const float* gamma,
+                               const float* beta, void* out, int64_t B, int64_t Cin, int64_t H, int64_t W, int64_t C1,
+                               float eps, int32_t out_dtype, int32_t gelu, xp_stream_t stream);
+
 /* -- a6: detector post ----------------------------------------------------------------
  * Replaces Softmax2d -> [:, :-1] -> PixelShuffle(r)   (XPoint.py:356-357).
  * logits (B, r*r+1, Hc, Wc) in `dtype` -> prob (B, 1, r*Hc, r*Wc) fp32.  r <= 8.

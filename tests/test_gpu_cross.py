@@ -193,3 +193,54 @@ def test_ss2d_fused_errors():
     with pytest.raises(RuntimeError):
         ss2d.ss2d_pack(torch.randn(1, 2, 4, 4))                  # no CPU path
     assert ss2d.ss2d_pack(torch.randn(0, 2, 4, 4, device=DEV)).shape == (0, 2, 2, 16)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# f2 glue kernels: add + bias + LayerNorm, patch-embed stem
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("C", [8, 48, 96, 100, 192, 384, 768, 1536])
+@pytest.mark.parametrize("mode", ["ln", "add_ln", "bias_ln", "add_only"])
+@pytest.mark.parametrize("xdt,ydt", [(torch.float32, torch.float32), (torch.float16, torch.float16), (torch.float16, torch.float32)])
+def test_add_layer_norm_vs_torch(C, mode, xdt, ydt):
+    """x = x + branch; n = LayerNorm(x) of VSSBlock (VMamba.py:1222-1234) / conv bias + LayerNorm of patch-embed and
+    downsample (VMamba.py:1405-1440) in one pass."""
+    from xpoint_b200.cross_scan import add_layer_norm
+    g = torch.Generator().manual_seed(C)
+    x = torch.randn(3, 7, 5, C, generator=g).to(xdt).to(DEV)
+    res = torch.randn(3, 7, 5, C, generator=g).to(DEV) if mode in ("add_ln", "add_only") else None
+    pb = torch.randn(C, generator=g).to(DEV) if mode == "bias_ln" else None
+    w = (1 + 0.1 * torch.randn(C, generator=g)).to(DEV)
+    b = (0.1 * torch.randn(C, generator=g)).to(DEV)
+    want_y = mode != "add_only"
+    s, y = add_layer_norm(x, res, w if want_y else None, b if want_y else None, 1e-5, y_dtype=ydt, pre_bias=pb,
+                          sum_dtype=torch.float32 if mode == "add_ln" else ydt, want_sum=mode in ("add_ln", "add_only"),
+                          want_y=want_y)
+    ref_s = x.float() + (res if res is not None else 0) + (pb if pb is not None else 0)
+    tol = 2e-6 if ydt == torch.float32 else 2e-3
+    if s is not None:
+        np.testing.assert_allclose(s.float().cpu().numpy(), ref_s.cpu().numpy(), rtol=tol, atol=tol)
+    if want_y:
+        ref = torch.nn.functional.layer_norm(ref_s, (C,), w, b, 1e-5)
+        np.testing.assert_allclose(y.float().cpu().numpy(), ref.cpu().numpy(), rtol=tol * 5, atol=tol * 5)
+        assert y.dtype == ydt
+
+
+@pytest.mark.parametrize("cin", [1, 3])
+@pytest.mark.parametrize("C1,H,W,odt", [(48, 64, 96, torch.float32), (48, 64, 96, torch.float16), (8, 33, 47, torch.float32),
+                                        (64, 16, 16, torch.bfloat16), (12, 20, 36, torch.float16)])
+def test_patch_embed_stem_vs_torch(cin, C1, H, W, odt):
+    """Conv2d(k3, s2, p1) + bias -> LayerNorm(C1) -> GELU, channel-last out (first half of patch-embed v2, VMamba.py:1405-1413)."""
+    from xpoint_b200.cross_scan import patch_embed_stem
+    g = torch.Generator().manual_seed(C1 + H)
+    img = torch.rand(2, cin, H, W, generator=g).to(DEV)
+    w = (0.3 * torch.randn(C1, cin, 3, 3, generator=g)).to(DEV)
+    b = (0.1 * torch.randn(C1, generator=g)).to(DEV)
+    lw = (1 + 0.1 * torch.randn(C1, generator=g)).to(DEV)
+    lb = (0.1 * torch.randn(C1, generator=g)).to(DEV)
+    out = patch_embed_stem(img, w, b, lw, lb, 1e-5, out_dtype=odt, gelu=True)
+    torch.backends.cudnn.allow_tf32 = False
+    ref = torch.nn.functional.conv2d(img, w, b, stride=2, padding=1).permute(0, 2, 3, 1)
+    ref = torch.nn.functional.gelu(torch.nn.functional.layer_norm(ref, (C1,), lw, lb, 1e-5))
+    assert out.shape == ref.shape and out.dtype == odt
+    tol = {torch.float32: 2e-5, torch.float16: 2e-3, torch.bfloat16: 1.6e-2}[odt]
+    np.testing.assert_allclose(out.float().cpu().numpy(), ref.cpu().numpy(), rtol=tol, atol=tol)

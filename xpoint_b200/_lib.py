@@ -50,6 +50,8 @@ _SIGNATURES = {
     "xp_ss2d_dwconv_pack": (ctypes.c_int, [c_void_p] * 4 + [c_int64] * 5 + [c_int32, c_int32, c_void_p]),
     "xp_ss2d_merge_norm": (ctypes.c_int, [c_void_p] * 5 + [c_int64] * 4 + [c_int32, c_float, c_void_p]),
     "xp_layer_norm": (ctypes.c_int, [c_void_p] * 4 + [c_int64, c_int64, c_int32, c_int32, c_float, c_void_p]),
+    "xp_add_layer_norm": (ctypes.c_int, [c_void_p] * 7 + [c_int64, c_int64] + [c_int32] * 4 + [c_float, c_void_p]),
+    "xp_patch_embed_stem": (ctypes.c_int, [c_void_p] * 6 + [c_int64] * 5 + [c_float, c_int32, c_int32, c_void_p]),
     "xp_detector_post": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32, c_void_p]),
     "xp_l2_normalize": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_void_p]),
     "xp_nms_workspace_bytes": (c_int64, [c_int64] * 3),

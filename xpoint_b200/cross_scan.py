@@ -146,3 +146,50 @@ def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: f
                                                 _lib.dtype_code(x), _lib.dtype_code(out), float(eps), _lib.stream_ptr(dev)))
         _lib.count_launches(1)
     return out
+
+
+def add_layer_norm(x: torch.Tensor, res, weight, bias, eps: float = 1e-5, y_dtype=None, pre_bias=None, sum_dtype=None,
+                   want_sum: bool = True, want_y: bool = True):
+    """One pass of ``s = x [+ res] [+ pre_bias]; y = LayerNorm(s)`` over channel-last rows (xp_add_layer_norm).
+
+    Returns ``(s or None, y or None)``.  x / res: (..., C) contiguous; weight / bias / pre_bias: (C)."""
+    dev = _lib.require_cuda(x, res, weight, bias, pre_bias)
+    x = x.contiguous()
+    C = x.shape[-1]
+    if res is not None:
+        res = res.contiguous()
+        if res.shape != x.shape:
+            raise RuntimeError("add_layer_norm: x and res must have the same shape")
+    s = torch.empty(x.shape, dtype=sum_dtype or (res.dtype if res is not None else x.dtype), device=dev) if want_sum else None
+    y = torch.empty(x.shape, dtype=y_dtype or x.dtype, device=dev) if want_y else None
+    if x.numel():
+        f32 = lambda t: None if t is None else t.float().contiguous()
+        w, b, pb = f32(weight), f32(bias), f32(pre_bias)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().xp_add_layer_norm(
+                _lib.ptr(x), _lib.ptr(res), _lib.ptr(pb), _lib.ptr(w), _lib.ptr(b), _lib.ptr(y), _lib.ptr(s), x.numel() // C, C,
+                _lib.dtype_code(x), _lib.dtype_code(res) if res is not None else 0, _lib.dtype_code(y) if y is not None else 0,
+                _lib.dtype_code(s) if s is not None else 0, float(eps), _lib.stream_ptr(dev)))
+        _lib.count_launches(1)
+    return s, y
+
+
+def patch_embed_stem(img: torch.Tensor, weight: torch.Tensor, bias, ln_weight, ln_bias, eps: float = 1e-5, out_dtype=None,
+                     gelu: bool = True) -> torch.Tensor:
+    """img (B, Cin, H, W) fp32, Cin in {1, 3}; weight (C1, Cin, 3, 3) -> (B, ceil(H/2), ceil(W/2), C1) channel-last:
+    Conv2d(k3, s2, p1) + bias + LayerNorm(C1) [+ GELU] in one kernel (xp_patch_embed_stem)."""
+    dev = _lib.require_cuda(img, weight, bias, ln_weight, ln_bias)
+    img = img.float().contiguous()
+    B, Cin, H, W = img.shape
+    C1 = weight.shape[0]
+    if tuple(weight.shape) != (C1, Cin, 3, 3):
+        raise RuntimeError("patch_embed_stem: weight must have shape (C1, Cin, 3, 3)")
+    out = torch.empty((B, (H + 1) // 2, (W + 1) // 2, C1), dtype=out_dtype or torch.float32, device=dev)
+    if out.numel():
+        f32 = lambda t: None if t is None else t.float().contiguous()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().xp_patch_embed_stem(_lib.ptr(img), _lib.ptr(f32(weight)), _lib.ptr(f32(bias)),
+                                                      _lib.ptr(f32(ln_weight)), _lib.ptr(f32(ln_bias)), _lib.ptr(out), B, Cin, H, W,
+                                                      C1, float(eps), _lib.dtype_code(out), int(bool(gelu)), _lib.stream_ptr(dev)))
+        _lib.count_launches(1)
+    return out

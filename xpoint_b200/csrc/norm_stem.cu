@@ -1,0 +1,224 @@
+// norm_stem.cu -- the glue kernels between the library GEMMs / convolutions of the VMamba encoder.
+//
+//  * xp_add_layer_norm: [residual add] + [per-channel bias] + LayerNorm in one pass over channel-last rows.
+//      VSSBlock computes x = x + branch; n = LayerNorm(x) twice per block (VMamba.py:1222-1234) and the patch-embed /
+//      downsample convolutions are followed by bias-add, permute and LayerNorm (VMamba.py:1405-1440): each of those is
+//      2-3 full passes over the activations in the reference; here it is one (read branch + residual, write the new
+//      residual and its normalised copy).
+//  * xp_patch_embed_stem: Conv2d(Cin -> C1, 3x3, stride 2, pad 1) + bias + LayerNorm(C1) + GELU, channel-last output
+//      (the first half of VMamba's patch-embed v2, VMamba.py:1405-1413), reading the image directly.
+#include "common.cuh"
+
+namespace xp {
+
+__device__ __forceinline__ float ld_as_f32(const void* p, int dt, int64_t i) {
+    if (dt == XP_F32) return reinterpret_cast<const float*>(p)[i];
+    if (dt == XP_F16) return __half2float(reinterpret_cast<const __half*>(p)[i]);
+    return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+}
+__device__ __forceinline__ void st_from_f32(void* p, int dt, int64_t i, float v) {
+    if (dt == XP_F32) reinterpret_cast<float*>(p)[i] = v;
+    else if (dt == XP_F16) reinterpret_cast<__half*>(p)[i] = __float2half_rn(v);
+    else reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+}
+
+struct AddLnParams {
+    const void* x; const void* res; const float* pre_bias; const float* gamma; const float* beta;
+    void* y; void* sum_out;
+    int64_t rows; int C; float eps;
+    int x_dt, res_dt, y_dt, sum_dt;
+};
+
+// warp per row, row held in registers (two-pass variance: torch's definition)
+template <int PER>
+__global__ void __launch_bounds__(256) add_layer_norm_kernel(const AddLnParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= p.rows) return;
+    const int C = p.C;
+    const int64_t o = row * C;
+    float v[PER];
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int c = lane + 32 * i;
+        float t = 0.0f;
+        if (c < C) {
+            t = ld_as_f32(p.x, p.x_dt, o + c);
+            if (p.res) t += ld_as_f32(p.res, p.res_dt, o + c);
+            if (p.pre_bias) t += p.pre_bias[c];
+            if (p.sum_out) st_from_f32(p.sum_out, p.sum_dt, o + c, t);
+        }
+        v[i] = t;
+        s += t;
+    }
+    if (!p.y) return;
+    const float mean = warp_sum(s) / (float)C;
+    float ss = 0.0f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const float d = (lane + 32 * i < C) ? v[i] - mean : 0.0f;
+        v[i] = d;
+        ss = fmaf(d, d, ss);
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / (float)C + p.eps);
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int c = lane + 32 * i;
+        if (c < C) st_from_f32(p.y, p.y_dt, o + c, fmaf(v[i] * rstd, p.gamma[c], p.beta[c]));
+    }
+}
+
+// ------------------------------------------------------------------------------------------ patch-embed stem
+// One thread = one output token, all C1 (<= 64) channels in registers; weights broadcast from shared memory.
+constexpr int STEM_MAXC = 64;
+
+template <int CIN>
+__global__ void __launch_bounds__(128) patch_embed_stem_kernel(const float* __restrict__ img, const float* __restrict__ wgt,
+                                                               const float* __restrict__ bias, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, void* __restrict__ out, int B,
+                                                               int H, int W, int C1, float eps, int out_dt, int gelu) {
+    __shared__ __align__(16) float sw[CIN * 9 * STEM_MAXC];     // [cin][tap][channel], channels padded to STEM_MAXC
+    __shared__ float sb[STEM_MAXC], sg[STEM_MAXC], sbe[STEM_MAXC];
+    const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;               // k3 s2 p1
+    for (int i = threadIdx.x; i < CIN * 9 * STEM_MAXC; i += blockDim.x) {
+        const int c = i % STEM_MAXC, tap = (i / STEM_MAXC) % 9, ci = i / (STEM_MAXC * 9);
+        sw[i] = c < C1 ? wgt[((int64_t)c * CIN + ci) * 9 + tap] : 0.0f;
+    }
+    for (int c = threadIdx.x; c < STEM_MAXC; c += blockDim.x) {
+        sb[c] = (c < C1 && bias) ? bias[c] : 0.0f;
+        sg[c] = c < C1 ? gamma[c] : 0.0f;
+        sbe[c] = c < C1 ? beta[c] : 0.0f;
+    }
+    __syncthreads();
+    const int64_t total = (int64_t)B * Ho * Wo;
+    const int64_t tok = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tok >= total) return;
+    const int wo = (int)(tok % Wo), ho = (int)((tok / Wo) % Ho);
+    const int64_t b = tok / ((int64_t)Wo * Ho);
+    float acc[STEM_MAXC];
+#pragma unroll
+    for (int c = 0; c < STEM_MAXC; ++c) acc[c] = sb[c];
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+        const float* plane = img + (b * CIN + ci) * (int64_t)H * W;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int h = 2 * ho - 1 + ky;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int w = 2 * wo - 1 + kx;
+                const float px = (h >= 0 && h < H && w >= 0 && w < W) ? __ldg(plane + (int64_t)h * W + w) : 0.0f;
+                const float4* wv = reinterpret_cast<const float4*>(sw + (ci * 9 + ky * 3 + kx) * STEM_MAXC);
+#pragma unroll
+                for (int q = 0; q < STEM_MAXC / 4; ++q) {
+                    if (4 * q < C1) {                      // uniform: skips the padded channel quads
+                        const float4 w4 = wv[q];
+                        acc[4 * q] = fmaf(px, w4.x, acc[4 * q]);
+                        acc[4 * q + 1] = fmaf(px, w4.y, acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(px, w4.z, acc[4 * q + 2]);
+                        acc[4 * q + 3] = fmaf(px, w4.w, acc[4 * q + 3]);
+                    }
+                }
+            }
+        }
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int c = 0; c < STEM_MAXC; ++c) s += c < C1 ? acc[c] : 0.0f;
+    const float mean = s / (float)C1;
+    float ss = 0.0f;
+#pragma unroll
+    for (int c = 0; c < STEM_MAXC; ++c) {
+        const float d = c < C1 ? acc[c] - mean : 0.0f;
+        acc[c] = d;
+        ss = fmaf(d, d, ss);
+    }
+    const float rstd = rsqrtf(ss / (float)C1 + eps);
+    const int64_t o = tok * C1;
+#pragma unroll
+    for (int c = 0; c < STEM_MAXC; ++c) {
+        if (c < C1) {
+            float v = fmaf(acc[c] * rstd, sg[c], sbe[c]);
+            if (gelu) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));     // exact (erf) GELU, nn.GELU default
+            acc[c] = v;
+        }
+    }
+    if (out_dt == XP_F32) {
+        float* dst = reinterpret_cast<float*>(out) + o;
+#pragma unroll
+        for (int c = 0; c < STEM_MAXC; ++c) if (c < C1) dst[c] = acc[c];
+    } else if (C1 % 8 == 0) {                               // 16-byte stores (o*2 bytes is 16-byte aligned when C1 % 8 == 0)
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(out) + o);
+#pragma unroll
+        for (int q = 0; q < STEM_MAXC / 8; ++q) {
+            if (8 * q < C1) {
+                uint4 raw;
+                if (out_dt == XP_F16) {
+                    __half2* h = reinterpret_cast<__half2*>(&raw);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(acc[8 * q + 2 * j], acc[8 * q + 2 * j + 1]);
+                } else {
+                    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(acc[8 * q + 2 * j], acc[8 * q + 2 * j + 1]);
+                }
+                dst[q] = raw;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < STEM_MAXC; ++c) if (c < C1) st_from_f32(out, out_dt, o + c, acc[c]);
+    }
+}
+
+}  // namespace xp
+
+using namespace xp;
+
+extern "C" int xp_add_layer_norm(const void* x, const void* res, const float* pre_bias, const float* gamma, const float* beta,
+                                 void* y, void* sum_out, int64_t rows, int64_t C, int32_t x_dtype, int32_t res_dtype,
+                                 int32_t y_dtype, int32_t sum_dtype, float eps, xp_stream_t stream) {
+    XP_REQUIRE(x, "xp_add_layer_norm: x is NULL");
+    XP_REQUIRE(y || sum_out, "xp_add_layer_norm: at least one of y / sum_out must be given");
+    XP_REQUIRE(!y || (gamma && beta), "xp_add_layer_norm: gamma / beta are required when y is given");
+    XP_REQUIRE(rows >= 0 && C > 0 && C <= 1536, "xp_add_layer_norm: need 0 < C <= 1536 (got %lld)", (long long)C);
+    for (int dt : {x_dtype, res ? res_dtype : XP_F32, y ? y_dtype : XP_F32, sum_out ? sum_dtype : XP_F32})
+        XP_REQUIRE(dt >= XP_F32 && dt <= XP_BF16, "xp_add_layer_norm: unsupported dtype %d", dt);
+    if (rows == 0) return XP_OK;
+    AddLnParams p{x, res, pre_bias, gamma, beta, y, sum_out, rows, (int)C, eps, x_dtype, res_dtype, y_dtype, sum_dtype};
+    const unsigned grid = (unsigned)ceil_div(rows, 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int per = (int)ceil_div(C, 32);
+    if (per <= 2) add_layer_norm_kernel<2><<<grid, 256, 0, st>>>(p);
+    else if (per <= 3) add_layer_norm_kernel<3><<<grid, 256, 0, st>>>(p);
+    else if (per <= 6) add_layer_norm_kernel<6><<<grid, 256, 0, st>>>(p);
+    else if (per <= 12) add_layer_norm_kernel<12><<<grid, 256, 0, st>>>(p);
+    else if (per <= 24) add_layer_norm_kernel<24><<<grid, 256, 0, st>>>(p);
+    else add_layer_norm_kernel<48><<<grid, 256, 0, st>>>(p);
+    XP_LAUNCH_CHECK("add_layer_norm_kernel");
+    return XP_OK;
+}
+
+extern "C" int xp_patch_embed_stem(const float* img, const float* weight, const float* bias, const float* gamma,
+                                   const float* beta, void* out, int64_t B, int64_t Cin, int64_t H, int64_t W, int64_t C1,
+                                   float eps, int32_t out_dtype, int32_t gelu, xp_stream_t stream) {
+    XP_REQUIRE(img && weight && gamma && beta && out, "xp_patch_embed_stem: NULL tensor pointer");
+    XP_REQUIRE(Cin == 1 || Cin == 3, "xp_patch_embed_stem: Cin must be 1 or 3 (got %lld)", (long long)Cin);
+    XP_REQUIRE(C1 > 0 && C1 <= STEM_MAXC && C1 % 4 == 0, "xp_patch_embed_stem: C1 must be a multiple of 4, <= %d (got %lld)",
+               STEM_MAXC, (long long)C1);
+    XP_REQUIRE(B >= 0 && H > 0 && W > 0, "xp_patch_embed_stem: bad shape");
+    XP_REQUIRE(out_dtype >= XP_F32 && out_dtype <= XP_BF16, "xp_patch_embed_stem: unsupported dtype %d", out_dtype);
+    if (B == 0) return XP_OK;
+    const int64_t total = B * ((H + 1) / 2) * ((W + 1) / 2);
+    const unsigned grid = (unsigned)ceil_div(total, 128);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (Cin == 1)
+        patch_embed_stem_kernel<1><<<grid, 128, 0, st>>>(img, weight, bias, gamma, beta, out, (int)B, (int)H, (int)W, (int)C1, eps,
+                                                          out_dtype, gelu);
+    else
+        patch_embed_stem_kernel<3><<<grid, 128, 0, st>>>(img, weight, bias, gamma, beta, out, (int)B, (int)H, (int)W, (int)C1, eps,
+                                                          out_dtype, gelu);
+    XP_LAUNCH_CHECK("patch_embed_stem_kernel");
+    return XP_OK;
+}

@@ -21,7 +21,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ss2d as _ss2d
-from .cross_scan import cross_scan_fn, layer_norm, merge_norm_gate
+from .cross_scan import add_layer_norm, cross_scan_fn, layer_norm, merge_norm_gate, patch_embed_stem
 from .selective_scan import scan_forward, selective_scan_fn
 
 
@@ -385,12 +385,91 @@ class VSSM(nn.Module):
         x = x.view(N, bs, bs, C // (bs * bs), H, W).permute(0, 3, 4, 1, 5, 2).contiguous()
         return x.view(N, C // (bs * bs), H * bs, W * bs)
 
-    def forward(self, x):
+    # ------------------------------------------------------------------------------------------------------------
+    # Forward.  Same math as VMamba.VSSM.forward (VMamba.py:1507-1525) with the glue between the library GEMMs /
+    # convolutions fused: the residual stream is carried as (x, pending branch) so that every
+    # `x = x + branch; n = norm(x)` pair is ONE xp_add_layer_norm pass; convolutions run channels-last so that the
+    # permutes around them are views, and their bias is added inside the LayerNorm pass that follows.
+    # ------------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _ln_dtype(for_matmul: bool):
+        if torch.is_autocast_enabled():
+            return torch.get_autocast_dtype("cuda") if for_matmul else torch.float32
+        return None
+
+    def _patch_embed(self, x):
+        pe = self.patch_embed
+        fast = (len(pe) == 8 and isinstance(pe[0], nn.Conv2d) and isinstance(pe[2], LayerNorm) and isinstance(pe[4], nn.GELU)
+                and pe[0].kernel_size == (3, 3) and pe[0].stride == (2, 2) and pe[0].padding == (1, 1)
+                and pe[0].out_channels <= 64 and pe[0].out_channels % 4 == 0 and x.dtype == torch.float32)
+        if not fast:
+            if self.in_chans == 3 and x.shape[1] == 1:
+                x = torch.cat((x, x, x), dim=1)
+            return pe(x)
+        conv1, ln1, conv2, ln2 = pe[0], pe[2], pe[5], pe[7]
+        w1 = conv1.weight
         if self.in_chans == 3 and x.shape[1] == 1:
-            x = torch.cat((x, x, x), dim=1)
-        x = self.patch_embed(x)
-        for layer in self.layers:
-            x = layer(x)
+            w1 = w1.sum(dim=1, keepdim=True)      # conv over three identical channels == conv with the summed kernel
+        cdt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
+        y = patch_embed_stem(x, w1, conv1.bias, ln1.weight, ln1.bias, ln1.eps, out_dtype=cdt, gelu=True)   # (B, H/2, W/2, C1)
+        y = F.conv2d(y.permute(0, 3, 1, 2), conv2.weight, None, conv2.stride, conv2.padding)              # channels-last in/out
+        y = y.permute(0, 2, 3, 1)
+        _, y = add_layer_norm(y, None, ln2.weight, ln2.bias, ln2.eps, y_dtype=self._ln_dtype(False) or y.dtype,
+                              pre_bias=conv2.bias, want_sum=False)
+        return y
+
+    @staticmethod
+    def _run_blocks(blocks, x):
+        """Returns (x, pending) with the block output = x + pending (pending may be None)."""
+        pend = None
+        for blk in blocks:
+            if not isinstance(blk, VSSBlock):
+                if pend is not None:
+                    x, pend = x + pend, None
+                x = blk(x)
+                continue
+            if blk.ssm_branch:
+                if pend is None:
+                    n = blk.norm(x)
+                else:
+                    x, n = add_layer_norm(pend, x, blk.norm.weight, blk.norm.bias, blk.norm.eps,
+                                          y_dtype=VSSM._ln_dtype(True) or x.dtype)
+                pend = blk.op(n)
+            if blk.mlp_branch:
+                if pend is None:
+                    n = blk.norm2(x)
+                else:
+                    x, n = add_layer_norm(pend, x, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps,
+                                          y_dtype=VSSM._ln_dtype(True) or x.dtype)
+                pend = blk.mlp(n)
+        return x, pend
+
+    def _downsample(self, ds, x, pend):
+        fast = (isinstance(ds, nn.Sequential) and len(ds) == 4 and isinstance(ds[1], nn.Conv2d) and isinstance(ds[3], LayerNorm))
+        if not fast:
+            if pend is not None:
+                x = x + pend
+            return ds(x)
+        conv, ln = ds[1], ds[3]
+        cdt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
+        if pend is not None:      # residual sum written once, already in the convolution's dtype and channels-last
+            x, _ = add_layer_norm(pend, x, None, None, sum_dtype=cdt, want_y=False)
+        elif x.dtype != cdt:
+            x = x.to(cdt)
+        y = F.conv2d(x.permute(0, 3, 1, 2), conv.weight, None, conv.stride, conv.padding).permute(0, 2, 3, 1)
+        _, y = add_layer_norm(y, None, ln.weight, ln.bias, ln.eps, y_dtype=self._ln_dtype(False) or y.dtype,
+                              pre_bias=conv.bias, want_sum=False)
+        return y
+
+    def forward(self, x):
+        x = self._patch_embed(x)
+        for i, layer in enumerate(self.layers):
+            x, pend = self._run_blocks(layer.blocks, x)
+            if isinstance(layer.downsample, nn.Identity):
+                if pend is not None:
+                    x = x + pend
+            else:
+                x = self._downsample(layer.downsample, x, pend)
         return self.depth_to_space(x.permute(0, 3, 1, 2), 4)
 
 

@@ -244,3 +244,17 @@ def test_patch_embed_stem_vs_torch(cin, C1, H, W, odt):
     assert out.shape == ref.shape and out.dtype == odt
     tol = {torch.float32: 2e-5, torch.float16: 2e-3, torch.bfloat16: 1.6e-2}[odt]
     np.testing.assert_allclose(out.float().cpu().numpy(), ref.cpu().numpy(), rtol=tol, atol=tol)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.float16, 2e-3), (torch.bfloat16, 1.6e-2)])
+@pytest.mark.parametrize("B,G,D,R,N,L", [(2, 4, 96, 6, 1, 1280), (1, 4, 24, 3, 2, 328), (3, 2, 40, 8, 4, 64), (1, 4, 16, 1, 1, 24)])
+def test_ss2d_dt_proj_vs_torch(dtype, tol, B, G, D, R, N, L):
+    """dt_proj of SS2D (VMamba.py:607-608) on a strided view of the x_proj output."""
+    from xpoint_b200 import ss2d
+    g = torch.Generator().manual_seed(R + L)
+    x_dbl = torch.randn(B, G, R + 2 * N, L, generator=g).to(dtype).to(DEV)
+    w = (0.4 * torch.randn(G, D, R, generator=g)).to(DEV)
+    out = ss2d.ss2d_dt_proj(x_dbl[:, :, :R], w)
+    ref = torch.einsum("gdr,bgrl->bgdl", w, x_dbl[:, :, :R].float())
+    assert out.dtype == dtype and out.shape == (B, G, D, L)
+    np.testing.assert_allclose(out.float().cpu().numpy(), ref.cpu().numpy(), rtol=tol, atol=tol)

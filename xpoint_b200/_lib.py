@@ -48,6 +48,7 @@ _SIGNATURES = {
                                                                          c_void_p]),
     "xp_ss2d_pack": (ctypes.c_int, [c_void_p, c_void_p] + [c_int64] * 4 + [c_int32, c_void_p]),
     "xp_ss2d_dwconv_pack": (ctypes.c_int, [c_void_p] * 4 + [c_int64] * 5 + [c_int32, c_int32, c_void_p]),
+    "xp_ss2d_dt_proj": (ctypes.c_int, [c_void_p] * 3 + [c_int64] * 8 + [c_int32, c_void_p]),
     "xp_ss2d_merge_norm": (ctypes.c_int, [c_void_p] * 5 + [c_int64] * 4 + [c_int32, c_float, c_void_p]),
     "xp_layer_norm": (ctypes.c_int, [c_void_p] * 4 + [c_int64, c_int64, c_int32, c_int32, c_float, c_void_p]),
     "xp_add_layer_norm": (ctypes.c_int, [c_void_p] * 7 + [c_int64, c_int64] + [c_int32] * 4 + [c_float, c_void_p]),

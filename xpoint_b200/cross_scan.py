@@ -134,18 +134,8 @@ def merge_norm_gate(ys: torch.Tensor, H: int, W: int, weight: torch.Tensor, bias
 
 
 def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5, out_dtype=None):
-    """LayerNorm over the last dimension of a channel-last tensor (xp_layer_norm)."""
-    dev = _lib.require_cuda(x, weight, bias)
-    x = x.contiguous()
-    C = x.shape[-1]
-    out = torch.empty(x.shape, dtype=out_dtype or x.dtype, device=dev)
-    if out.numel():
-        with torch.cuda.device(dev):
-            _lib.check(_lib.lib().xp_layer_norm(_lib.ptr(x), _lib.ptr(weight.float().contiguous()),
-                                                _lib.ptr(bias.float().contiguous()), _lib.ptr(out), x.numel() // C, C,
-                                                _lib.dtype_code(x), _lib.dtype_code(out), float(eps), _lib.stream_ptr(dev)))
-        _lib.count_launches(1)
-    return out
+    """LayerNorm over the last dimension of a channel-last tensor (the no-residual case of xp_add_layer_norm)."""
+    return add_layer_norm(x, None, weight, bias, eps, y_dtype=out_dtype or x.dtype, want_sum=False)[1]
 
 
 def add_layer_norm(x: torch.Tensor, res, weight, bias, eps: float = 1e-5, y_dtype=None, pre_bias=None, sum_dtype=None,

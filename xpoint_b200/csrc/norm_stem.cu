@@ -29,9 +29,82 @@ struct AddLnParams {
     int x_dt, res_dt, y_dt, sum_dt;
 };
 
-// warp per row, row held in registers (two-pass variance: torch's definition)
+__device__ __forceinline__ float4 ld4_as_f32(const void* p, int dt, int64_t i4) {     // elements 4*i4 .. 4*i4+3
+    if (dt == XP_F32) return __ldg(reinterpret_cast<const float4*>(p) + i4);
+    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p) + i4);
+    if (dt == XP_F16) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+        return make_float4(a.x, a.y, b.x, b.y);
+    }
+    return make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u), __uint_as_float(raw.y << 16),
+                       __uint_as_float(raw.y & 0xffff0000u));
+}
+__device__ __forceinline__ void st4_from_f32(void* p, int dt, int64_t i4, float4 v) {
+    if (dt == XP_F32) { reinterpret_cast<float4*>(p)[i4] = v; return; }
+    uint2 raw;
+    if (dt == XP_F16) {
+        *reinterpret_cast<__half2*>(&raw.x) = __floats2half2_rn(v.x, v.y);
+        *reinterpret_cast<__half2*>(&raw.y) = __floats2half2_rn(v.z, v.w);
+    } else {
+        *reinterpret_cast<__nv_bfloat162*>(&raw.x) = __floats2bfloat162_rn(v.x, v.y);
+        *reinterpret_cast<__nv_bfloat162*>(&raw.y) = __floats2bfloat162_rn(v.z, v.w);
+    }
+    reinterpret_cast<uint2*>(p)[i4] = raw;
+}
+
+// LPR lanes per row (power of two), each lane owns CH interleaved 4-element chunks held in registers; a warp covers
+// 32 / LPR rows, so short rows (C = 48 .. 192) still move 8-16 bytes per lane per access.  Two-pass variance (torch).
+template <int CH>
+__global__ void __launch_bounds__(256) add_layer_norm_kernel(const AddLnParams p, int lpr) {
+    const int lane = threadIdx.x & 31;
+    const int sub = lane & (lpr - 1), rows_per_warp = 32 / lpr;
+    const int64_t row = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * rows_per_warp + lane / lpr;
+    const bool live = row < p.rows;
+    const int nch = p.C >> 2;                       // chunks per row (C % 4 == 0)
+    const int64_t o4 = row * nch;
+    float4 v[CH];
+    float s = 0.0f;
+#pragma unroll
+    for (int q = 0; q < CH; ++q) {
+        const int c4 = q * lpr + sub;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live && c4 < nch) {
+            t = ld4_as_f32(p.x, p.x_dt, o4 + c4);
+            if (p.res) { const float4 r = ld4_as_f32(p.res, p.res_dt, o4 + c4); t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w; }
+            if (p.pre_bias) { const float4 r = __ldg(reinterpret_cast<const float4*>(p.pre_bias) + c4); t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w; }
+            if (p.sum_out) st4_from_f32(p.sum_out, p.sum_dt, o4 + c4, t);
+        }
+        v[q] = t;
+        s += (t.x + t.y) + (t.z + t.w);
+    }
+    if (!p.y) return;
+    for (int o = lpr >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)p.C;
+    float ss = 0.0f;
+#pragma unroll
+    for (int q = 0; q < CH; ++q) {
+        if (q * lpr + sub < nch) {
+            v[q].x -= mean; v[q].y -= mean; v[q].z -= mean; v[q].w -= mean;
+            ss = fmaf(v[q].x, v[q].x, fmaf(v[q].y, v[q].y, fmaf(v[q].z, v[q].z, fmaf(v[q].w, v[q].w, ss))));
+        }
+    }
+    for (int o = lpr >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss / (float)p.C + p.eps);
+#pragma unroll
+    for (int q = 0; q < CH; ++q) {
+        const int c4 = q * lpr + sub;
+        if (live && c4 < nch) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma) + c4), b = __ldg(reinterpret_cast<const float4*>(p.beta) + c4);
+            st4_from_f32(p.y, p.y_dt, o4 + c4, make_float4(fmaf(v[q].x * rstd, g.x, b.x), fmaf(v[q].y * rstd, g.y, b.y),
+                                                            fmaf(v[q].z * rstd, g.z, b.z), fmaf(v[q].w * rstd, g.w, b.w)));
+        }
+    }
+}
+
+// scalar fallback (C % 4 != 0 or unaligned pointers): warp per row
 template <int PER>
-__global__ void __launch_bounds__(256) add_layer_norm_kernel(const AddLnParams p) {
+__global__ void __launch_bounds__(256) add_layer_norm_scalar_kernel(const AddLnParams p) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= p.rows) return;
@@ -187,15 +260,28 @@ extern "C" int xp_add_layer_norm(const void* x, const void* res, const float* pr
         XP_REQUIRE(dt >= XP_F32 && dt <= XP_BF16, "xp_add_layer_norm: unsupported dtype %d", dt);
     if (rows == 0) return XP_OK;
     AddLnParams p{x, res, pre_bias, gamma, beta, y, sum_out, rows, (int)C, eps, x_dtype, res_dtype, y_dtype, sum_dtype};
-    const unsigned grid = (unsigned)ceil_div(rows, 8);
     cudaStream_t st = (cudaStream_t)stream;
-    const int per = (int)ceil_div(C, 32);
-    if (per <= 2) add_layer_norm_kernel<2><<<grid, 256, 0, st>>>(p);
-    else if (per <= 3) add_layer_norm_kernel<3><<<grid, 256, 0, st>>>(p);
-    else if (per <= 6) add_layer_norm_kernel<6><<<grid, 256, 0, st>>>(p);
-    else if (per <= 12) add_layer_norm_kernel<12><<<grid, 256, 0, st>>>(p);
-    else if (per <= 24) add_layer_norm_kernel<24><<<grid, 256, 0, st>>>(p);
-    else add_layer_norm_kernel<48><<<grid, 256, 0, st>>>(p);
+    bool vec = C % 4 == 0;
+    for (const void* q : {x, res, (const void*)pre_bias, (const void*)gamma, (const void*)beta, (const void*)y, (const void*)sum_out})
+        vec = vec && (reinterpret_cast<uintptr_t>(q) & 15) == 0;
+    if (vec) {
+        const int nch = (int)(C / 4);
+        int lpr = 2;
+        while (lpr < 32 && lpr * 3 < nch) lpr <<= 1;          // <= 3 chunks per lane until the warp is one row wide
+        const int ch = (nch + lpr - 1) / lpr;
+        const unsigned grid = (unsigned)ceil_div(rows, 8 * (32 / lpr));
+        if (ch <= 1) add_layer_norm_kernel<1><<<grid, 256, 0, st>>>(p, lpr);
+        else if (ch <= 2) add_layer_norm_kernel<2><<<grid, 256, 0, st>>>(p, lpr);
+        else if (ch <= 3) add_layer_norm_kernel<3><<<grid, 256, 0, st>>>(p, lpr);
+        else if (ch <= 6) add_layer_norm_kernel<6><<<grid, 256, 0, st>>>(p, lpr);
+        else add_layer_norm_kernel<12><<<grid, 256, 0, st>>>(p, lpr);
+    } else {
+        const unsigned grid = (unsigned)ceil_div(rows, 8);
+        const int per = (int)ceil_div(C, 32);
+        if (per <= 3) add_layer_norm_scalar_kernel<3><<<grid, 256, 0, st>>>(p);
+        else if (per <= 12) add_layer_norm_scalar_kernel<12><<<grid, 256, 0, st>>>(p);
+        else add_layer_norm_scalar_kernel<48><<<grid, 256, 0, st>>>(p);
+    }
     XP_LAUNCH_CHECK("add_layer_norm_kernel");
     return XP_OK;
 }

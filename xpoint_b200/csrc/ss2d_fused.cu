@@ -348,6 +348,54 @@ __global__ void __launch_bounds__(256) ss2d_merge_norm_kernel(const float* __res
     }
 }
 
+// ------------------------------------------------------------------------------------------ dt projection (rank <= 8)
+// delta[b, g, d, l] = sum_r W[g, d, r] * dts_r[b, g, r, l]   (VMamba.py:607-608 / :325: dt_proj as a grouped 1x1 conv).
+// With dt_rank = ceil(d_model / 16) <= 8 this is an outer-product-sized contraction whose cost is writing delta: a
+// library GEMM runs it at a quarter of the HBM rate, here every thread keeps its 8 tokens of the R rank rows in
+// registers and streams 16-byte stores over the channel rows.
+template <typename T>
+__global__ void __launch_bounds__(256) ss2d_dt_proj_kernel(const T* __restrict__ xr, const float* __restrict__ Wt, T* __restrict__ out,
+                                                           int G, int D, int R, int64_t L, int64_t x_bs, int64_t x_gs,
+                                                           int64_t x_rs) {
+    constexpr int VEC = 16 / (int)sizeof(T);          // tokens per thread (8 for 16-bit, 4 for fp32)
+    const int tg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int64_t bg = blockIdx.y;
+    const int64_t b = bg / G, g = bg % G;
+    const int64_t l0 = ((int64_t)blockIdx.x * 32 + tg) * VEC;
+    if (l0 >= L) return;                               // L % VEC == 0: token groups are all-or-nothing
+    float x[8][VEC];
+    const T* src = xr + b * x_bs + g * x_gs + l0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        if (r < R) {
+            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(src + r * x_rs));
+            const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) x[r][j] = to_f32(e[j]);
+        }
+    }
+    const float* Wg = Wt + g * (int64_t)D * R;
+    T* dst = out + (bg * D) * L + l0;
+    for (int d = rl; d < D; d += 8) {
+        float acc[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] = 0.0f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            if (r < R) {
+                const float w = __ldg(Wg + (int64_t)d * R + r);
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) acc[j] = fmaf(w, x[r][j], acc[j]);
+            }
+        }
+        uint4 raw;
+        T* e = reinterpret_cast<T*>(&raw);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) e[j] = from_f32<T>(acc[j]);
+        *reinterpret_cast<uint4*>(dst + (int64_t)d * L) = raw;
+    }
+}
+
 template <typename TO, int TH, int TW, int DPER>
 static int merge_norm_launch_d(const float* ys, const float* gamma, const float* beta, const void* zact, void* out, int64_t B,
                                int64_t D, int64_t H, int64_t W, float eps, cudaStream_t st) {
@@ -445,4 +493,29 @@ extern "C" int xp_ss2d_merge_norm(const float* ys, const float* gamma, const flo
         case XP_F16: return merge_norm_dispatch<__half>(ys, gamma, beta, zact, out, B, D, H, W, eps, st);
         default: return merge_norm_dispatch<__nv_bfloat16>(ys, gamma, beta, zact, out, B, D, H, W, eps, st);
     }
+}
+
+extern "C" int xp_ss2d_dt_proj(const void* dts_r, const float* weight, void* delta, int64_t B, int64_t G, int64_t D, int64_t R,
+                               int64_t L, int64_t x_batch_stride, int64_t x_group_stride, int64_t x_rank_stride, int32_t dtype,
+                               xp_stream_t stream) {
+    XP_REQUIRE(dts_r && weight && delta, "xp_ss2d_dt_proj: NULL tensor pointer");
+    XP_REQUIRE(B >= 0 && G > 0 && D > 0 && L > 0, "xp_ss2d_dt_proj: bad shape");
+    XP_REQUIRE(R >= 1 && R <= 8, "xp_ss2d_dt_proj: dt_rank must be in 1..8 (got %lld)", (long long)R);
+    XP_REQUIRE(dtype >= XP_F32 && dtype <= XP_BF16, "xp_ss2d_dt_proj: unsupported dtype %d", dtype);
+    const int64_t vec = dtype == XP_F32 ? 4 : 8;
+    XP_REQUIRE(L % vec == 0 && x_batch_stride % vec == 0 && x_group_stride % vec == 0 && x_rank_stride % vec == 0 &&
+                   (reinterpret_cast<uintptr_t>(dts_r) & 15) == 0 && (reinterpret_cast<uintptr_t>(delta) & 15) == 0,
+               "xp_ss2d_dt_proj: rows must be 16-byte aligned (L and strides multiples of %lld elements)", (long long)vec);
+    XP_REQUIRE(B * G <= 65535, "xp_ss2d_dt_proj: batch * groups must be <= 65535");
+    if (B == 0) return XP_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((unsigned)ceil_div(L, 32 * vec), (unsigned)(B * G));
+#define XP_DT(T) ss2d_dt_proj_kernel<T><<<grid, 256, 0, st>>>((const T*)dts_r, weight, (T*)delta, (int)G, (int)D, (int)R, L, \
+                                                               x_batch_stride, x_group_stride, x_rank_stride)
+    if (dtype == XP_F32) XP_DT(float);
+    else if (dtype == XP_F16) XP_DT(__half);
+    else XP_DT(__nv_bfloat16);
+#undef XP_DT
+    XP_LAUNCH_CHECK("ss2d_dt_proj_kernel");
+    return XP_OK;
 }

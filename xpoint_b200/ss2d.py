@@ -74,6 +74,27 @@ def ss2d_merge_norm(ys: torch.Tensor, H: int, W: int, weight: torch.Tensor, bias
     return out
 
 
+def ss2d_dt_proj(dts_r: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """dts_r (B, G, R, L) (a strided view of the x_proj output), weight (G, D, R) fp32 -> delta (B, G, D, L)."""
+    dev = _lib.require_cuda(dts_r, weight)
+    B, G, R, L = dts_r.shape
+    D = weight.shape[1]
+    if dts_r.stride(3) != 1 or tuple(weight.shape) != (G, D, R) or weight.dtype != torch.float32:
+        raise RuntimeError("ss2d_dt_proj expects dts_r (B, G, R, L) with unit token stride and fp32 weight (G, D, R)")
+    out = torch.empty((B, G, D, L), dtype=dts_r.dtype, device=dev)
+    if out.numel():
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().xp_ss2d_dt_proj(_lib.ptr(dts_r), _lib.ptr(weight.contiguous()), _lib.ptr(out), B, G, D, R, L,
+                                                  dts_r.stride(0), dts_r.stride(1), dts_r.stride(2), _lib.dtype_code(dts_r),
+                                                  _lib.stream_ptr(dev)))
+        _lib.count_launches(1)
+    return out
+
+
+def dt_proj_supported(R: int, L: int, dtype: torch.dtype, batch_groups: int) -> bool:
+    return R <= 8 and L % (4 if dtype == torch.float32 else 8) == 0 and batch_groups <= 65535
+
+
 def fused_supported(H: int, W: int, D: int, d_state: int) -> bool:
     """Shapes the copy-free path covers (the rest takes the CrossScan -> scan -> CrossMerge kernels)."""
     return H % 4 == 0 and W % 4 == 0 and D <= 3072 and d_state <= 2

@@ -215,6 +215,7 @@ class SS2D(nn.Module):
             w = dict(
                 wx=wx.expand(batch, -1, -1, -1).contiguous(),                     # (B, 2, 2(R+2N), D)
                 wdt=wdt.expand(batch, -1, -1, -1, -1).contiguous(),               # (B, 2, 2, D, R)
+                wdt32=self.dt_projs_weight.detach().float()[order].contiguous(),  # (4, D, R) for xp_ss2d_dt_proj
                 A=(-self.A_logs.detach().float().exp()).view(K, D, N)[order].reshape(K * D, N).contiguous(),
                 Ds=self.Ds.detach().float().view(K, D)[order].reshape(-1).contiguous(),
                 dt_bias=self.dt_projs_bias.detach().float()[order].reshape(-1).contiguous(),
@@ -235,9 +236,11 @@ class SS2D(nn.Module):
         K, N, R = self.k_group, self.d_state, self.dt_rank
         w = self._fused_weights(B, xx.dtype)
         x_dbl = torch.matmul(w["wx"], xx)                                          # (B, 2, 2(R+2N), L)
-        x_dbl = x_dbl.view(B, 2, 2, R + 2 * N, L)
-        dts = torch.matmul(w["wdt"], x_dbl[:, :, :, :R])                           # (B, 2, 2, D, L)
         x_dbl = x_dbl.view(B, K, R + 2 * N, L)
+        if _ss2d.dt_proj_supported(R, L, x_dbl.dtype, B * K):
+            dts = _ss2d.ss2d_dt_proj(x_dbl[:, :, :R], w["wdt32"])                  # (B, 4, D, L), store-bound kernel
+        else:
+            dts = torch.matmul(w["wdt"], x_dbl.view(B, 2, 2, R + 2 * N, L)[:, :, :, :R])   # (B, 2, 2, D, L)
         ys, _ = scan_forward(xx.view(B, 2 * D, L), dts.view(B, K * D, L), w["A"], x_dbl[:, :, R:R + N], x_dbl[:, :, R + N:],
                              w["Ds"], None, w["dt_bias"], True, True, u_group_div=2,
                              reverse_group_mask=_ss2d.REVERSE_MASK)               # (B, 4*D, L) fp32, natural order

@@ -19,7 +19,10 @@
 //   warp 2   TMEM allocation (512 columns) and release.
 //   warps 4-7 epilogue: thread = accumulator row; tcgen05.ld 32 columns at a time, key = |y_j|^2 - 2 acc,
 //            running (min, argmin) in registers (ascending j, strict <: lowest index wins ties).
-// The column arg-min is the same kernel with X and Y swapped.
+// The column arg-min  nn_y[j] = argmin_i ( |x_i|^2 - 2 <x_i, y_j> )  comes out of the SAME accumulator tile (the
+// similarity GEMM runs once, not twice): per column the 32 rows of a warp are reduced with two REDUX.MIN
+// (order-preserving uint key, then the lowest row holding it), lane t keeps column t, and one 64-bit
+// red.global.min of (key << 32 | row) per lane and 32-column chunk merges warps and row blocks.
 #include "common.cuh"
 
 namespace xp {
@@ -112,7 +115,8 @@ __global__ void __launch_bounds__(256, 1)
 nn_argmin_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__ CUtensorMap map_xlo,
                     const __grid_constant__ CUtensorMap map_yhi, const __grid_constant__ CUtensorMap map_ylo,
                     const float* __restrict__ ynorm, const int32_t* __restrict__ nx, const int32_t* __restrict__ ny,
-                    int x_stride, int y_stride, int C, int32_t* __restrict__ nn) {
+                    int x_stride, int y_stride, int C, int32_t* __restrict__ nn, const float* __restrict__ xnorm,
+                    unsigned long long* __restrict__ colkey) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* yn_s = reinterpret_cast<float*>(base + TC_STAGES * TC_STAGE_BYTES);            // [2][TC_BN]
@@ -195,6 +199,10 @@ nn_argmin_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_co
             float best = INFINITY;
             int bestj = 0x7fffffff;
             const float* yn = ynorm + (int64_t)pair * y_stride;
+            const bool row_valid = i0 + row < n_x;
+            const float xn = (colkey && row_valid) ? xnorm[(int64_t)pair * x_stride + i0 + row] : INFINITY;   // +inf: never the min
+            const unsigned my_row = row_valid ? (unsigned)(i0 + row) : 0x7fffffffu;
+            unsigned long long* ck = colkey ? colkey + (int64_t)pair * y_stride : nullptr;
             for (int jt = 0; jt < n_tiles; ++jt) {
                 const int buf = jt & 1;
                 // stage |y_j|^2 of this column tile (128 epilogue threads x 2 values)
@@ -217,6 +225,19 @@ nn_argmin_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_co
                         const float key = fmaf(-2.0f, v[t], yn_s[buf * TC_BN + c * 32 + t]);   // +inf past n_y
                         if (key < best) { best = key; bestj = jt * TC_BN + c * 32 + t; }
                     }
+                    if (ck) {
+                        unsigned cm = 0xffffffffu, ci = 0x7fffffffu;
+#pragma unroll
+                        for (int t = 0; t < 32; ++t) {
+                            const unsigned u = __float_as_uint(fmaf(-2.0f, v[t], xn));
+                            const unsigned k = u ^ ((unsigned)((int)u >> 31) | 0x80000000u);   // order-preserving float -> uint
+                            const unsigned m = __reduce_min_sync(0xffffffffu, k);
+                            const unsigned who = __reduce_min_sync(0xffffffffu, k == m ? my_row : 0x7fffffffu);
+                            if (lane == t) { cm = m; ci = who; }
+                        }
+                        const int j = jt * TC_BN + c * 32 + lane;
+                        if (j < n_y && ci != 0x7fffffffu) atomicMin(ck + j, ((unsigned long long)cm << 32) | ci);
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -233,7 +254,7 @@ nn_argmin_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_co
 // ---------------------------------------------------------------------------------- host
 static int tc_direction(const float* Xhi, const float* Xlo, const float* Yhi, const float* Ylo, const float* ynorm,
                         const int32_t* nx, const int32_t* ny, int64_t P, int64_t x_stride, int64_t y_stride, int64_t C,
-                        int32_t* nn, cudaStream_t st) {
+                        int32_t* nn, const float* xnorm, unsigned long long* colkey, cudaStream_t st) {
     CUtensorMap mxh, mxl, myh, myl;
     const uint64_t xdims[2] = {(uint64_t)C, (uint64_t)(P * x_stride)}, ydims[2] = {(uint64_t)C, (uint64_t)(P * y_stride)};
     const uint64_t strides[1] = {(uint64_t)C * 4};
@@ -245,13 +266,23 @@ static int tc_direction(const float* Xhi, const float* Xlo, const float* Yhi, co
     if ((rc = make_tensor_map(&myl, XP_F32, 2, Ylo, ydims, strides, ybox, 1))) return rc;
     XP_CUDA_OK(cudaFuncSetAttribute(nn_argmin_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     dim3 grid((unsigned)ceil_div(x_stride, TC_BM), (unsigned)P);
-    nn_argmin_tc_kernel<<<grid, 256, TC_SMEM, st>>>(mxh, mxl, myh, myl, ynorm, nx, ny, (int)x_stride, (int)y_stride, (int)C, nn);
+    nn_argmin_tc_kernel<<<grid, 256, TC_SMEM, st>>>(mxh, mxl, myh, myl, ynorm, nx, ny, (int)x_stride, (int)y_stride, (int)C, nn,
+                                                    xnorm, colkey);
     XP_LAUNCH_CHECK("nn_argmin_tc_kernel");
     return XP_OK;
 }
 
 int64_t mnn_tc_workspace_bytes(int64_t P, int64_t x_stride, int64_t y_stride, int64_t C) {
-    return 2 * (P * x_stride + P * y_stride) * C * 4 + 1024;
+    return 2 * (P * x_stride + P * y_stride) * C * 4 + P * y_stride * 8 + 1024;   // hi/lo copies + column keys
+}
+
+// column keys (key << 32 | row) -> nn_y; untouched columns (no valid row / column past n_y) stay -1
+__global__ void __launch_bounds__(256) decode_colkey_kernel(const unsigned long long* __restrict__ colkey, int32_t* __restrict__ nn_y,
+                                                            int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k = colkey[i];
+    nn_y[i] = k == ~0ull ? -1 : (int32_t)(k & 0xffffffffu);
 }
 
 int mnn_argmin_tc(const float* X, const float* Y, const int32_t* nx, const int32_t* ny, int64_t P, int64_t x_stride,
@@ -268,11 +299,18 @@ int mnn_argmin_tc(const float* X, const float* Y, const int32_t* nx, const int32
     XP_LAUNCH_CHECK("split_tf32_kernel");
     split_tf32_kernel<<<(unsigned)ceil_div(nye / 4, 256), 256, 0, st>>>(Y, Yhi, Ylo, nye);
     XP_LAUNCH_CHECK("split_tf32_kernel");
+    unsigned long long* colkey = reinterpret_cast<unsigned long long*>(ws + 2 * nxe + 2 * nye);
     XP_CUDA_OK(cudaMemsetAsync(nn_x, 0xff, sizeof(int32_t) * P * x_stride, st));
-    XP_CUDA_OK(cudaMemsetAsync(nn_y, 0xff, sizeof(int32_t) * P * y_stride, st));
-    int rc = tc_direction(Xhi, Xlo, Yhi, Ylo, ynorm, nx, ny, P, x_stride, y_stride, C, nn_x, st);
+    XP_CUDA_OK(cudaMemsetAsync(colkey, 0xff, sizeof(unsigned long long) * P * y_stride, st));
+    // one similarity GEMM: row arg-min in registers, column arg-min through REDUX + 64-bit atomic min
+    int rc = tc_direction(Xhi, Xlo, Yhi, Ylo, ynorm, nx, ny, P, x_stride, y_stride, C, nn_x, xnorm, colkey, st);
     if (rc) return rc;
-    return tc_direction(Yhi, Ylo, Xhi, Xlo, xnorm, ny, nx, P, y_stride, x_stride, C, nn_y, st);
+    const int64_t ncol = P * y_stride;
+    if (ncol) {
+        decode_colkey_kernel<<<(unsigned)ceil_div(ncol, 256), 256, 0, st>>>(colkey, nn_y, ncol);
+        XP_LAUNCH_CHECK("decode_colkey_kernel");
+    }
+    return XP_OK;
 }
 
 }  // namespace xp

@@ -132,13 +132,74 @@ class XPoint(nn.Module):
             return pp.normalize_descriptors(x)
         return x.to(torch.float)
 
+    # -- inference-time form of the two heads (XPoint.py:112-138, 348-371) -------------------------------------------
+    # pad -> conv3x3 -> ReLU -> BN -> conv1x1 -> BN, twice on the same input.  In eval mode both BatchNorms are affine
+    # maps, so they fold into the 1x1 convolution:  W2' = diag(s2) W2 diag(s1),  b2' = s2 * (W2 t1 + b2) + t2  with
+    # s = gamma / sqrt(var + eps), t = beta - mean * s.  The two 3x3 convolutions share their input and run as ONE
+    # channels-last convolution with 512 outputs; the 1x1 convolutions are GEMMs with the bias in the epilogue.
+    def _heads_foldable(self):
+        c = self.config
+        if self.training or c["bn_first"] or not c["final_batchnorm"] or not c["descriptor_head"] or not c["normalize_descriptors"]:
+            return False
+        d = self.detector_head_convolutions
+        return len(d) == 6 and isinstance(d[3], nn.BatchNorm2d) and isinstance(d[5], nn.BatchNorm2d)
+
+    def _folded_heads(self):
+        mods = list(self.detector_head_convolutions) + list(self.descriptor_head_convolutions)
+        params = [t for m in mods for t in list(m.parameters()) + list(m.buffers())]
+        key = tuple((t.data_ptr(), t._version) for t in params)
+        cache = getattr(self, "_head_cache", None)
+        if cache is not None and cache[0] == key:
+            return cache[1]
+
+        def fold(seq):
+            conv1, bn1, conv2, bn2 = seq[1], seq[3], seq[4], seq[5]
+            s1 = bn1.weight.float() / torch.sqrt(bn1.running_var.float() + bn1.eps)
+            t1 = bn1.bias.float() - bn1.running_mean.float() * s1
+            s2 = bn2.weight.float() / torch.sqrt(bn2.running_var.float() + bn2.eps)
+            t2 = bn2.bias.float() - bn2.running_mean.float() * s2
+            W2 = conv2.weight.float().flatten(1)                                  # (out, 256)
+            b2 = conv2.bias.float() if conv2.bias is not None else torch.zeros_like(s2)
+            return conv1.weight.float(), conv1.bias.float(), (s2[:, None] * W2 * s1[None, :]).contiguous(), s2 * (W2 @ t1 + b2) + t2
+
+        with torch.no_grad():
+            w1d, b1d, w2d, b2d = fold(self.detector_head_convolutions)
+            w1s, b1s, w2s, b2s = fold(self.descriptor_head_convolutions)
+            folded = dict(w1=torch.cat([w1d, w1s]).contiguous(memory_format=torch.channels_last), b1=torch.cat([b1d, b1s]),
+                          w2_det=w2d.t().contiguous(), b2_det=b2d, w2_desc=w2s.t().contiguous(), b2_desc=b2s, n1=w1d.shape[0])
+        self._head_cache = (key, folded)
+        return folded
+
+    def _heads_fused(self, x):
+        f = self._folded_heads()
+        cdt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
+        Bn, _, Hc, Wc = x.shape
+        xp = self.detector_head_convolutions[0](x).to(dtype=cdt, memory_format=torch.channels_last)   # pad once for both heads
+        y = nn.functional.conv2d(xp, f["w1"].to(cdt)).permute(0, 2, 3, 1)                            # (B, Hc, Wc, 512)
+        y = torch.relu_(y + f["b1"].to(cdt)).reshape(-1, y.shape[-1])
+        n1 = f["n1"]
+        logits = torch.addmm(f["b2_det"].to(cdt), y[:, :n1], f["w2_det"].to(cdt))                   # (rows, 65)
+        draw = torch.addmm(f["b2_desc"].to(cdt), y[:, n1:], f["w2_desc"].to(cdt))                   # (rows, 256)
+        logits = logits.view(Bn, Hc, Wc, -1).permute(0, 3, 1, 2).contiguous()
+        draw = draw.view(Bn, Hc, Wc, -1).permute(0, 3, 1, 2).contiguous()
+        if self.config["force_return_logits"]:
+            prob, lg = None, logits.to(torch.float)
+        else:
+            prob, lg = pp.detector_post(logits, self.encoder_downsample_ratio), None
+        desc, desc_cl = pp.normalize_descriptors(draw, channel_last_copy=True)
+        return prob, lg, desc, desc_cl
+
     def forward_impl(self, data):  # XPoint.py:283-323
         x = self.encoder(data["image"])
         out = {"prob": None, "logits": None}
         encoder_output = x.clone().detach()
-        out["prob"], out["logits"] = self.detector_head(x)
-        if self.config["descriptor_head"]:
-            out["desc"] = self.descriptor_head(x)
+        if self._heads_foldable():
+            # desc_cl: the same unit descriptors as (B, Hc, Wc, 256) -- the layout the sampler gathers 1 KiB rows from
+            out["prob"], out["logits"], out["desc"], out["desc_cl"] = self._heads_fused(x)
+        else:
+            out["prob"], out["logits"] = self.detector_head(x)
+            if self.config["descriptor_head"]:
+                out["desc"] = self.descriptor_head(x)
         out["encoder_output"] = encoder_output
         return out
 
@@ -185,15 +246,16 @@ class PairPipeline:
         self.nms, self.thr, self.iou, self.topk = nms, detection_threshold, iou, keep_top_k
         self.use_tensor_cores = use_tensor_cores
 
-    def tail(self, prob_o, prob_t, desc_o, desc_t) -> PairResult:
-        """prob (B,1,H,W) fp32; desc (B,256,Hc,Wc) fp32 -> keypoints, descriptors and mutual matches."""
+    def tail(self, prob_o, prob_t, desc_o, desc_t, channel_last=False) -> PairResult:
+        """prob (B,1,H,W) fp32; desc (B,256,Hc,Wc) fp32 [or (B,Hc,Wc,256) with channel_last] -> keypoints, descriptors
+        and mutual matches."""
         B, _, H, W = prob_o.shape
         prob = torch.cat([prob_o, prob_t], 0).reshape(2 * B, H, W)
         kps = pp.nms_keypoints(prob, self.nms, self.thr, self.iou, self.topk, kp_threshold=self.thr, capacity=self.topk,
                                want_map=False)
         count = torch.clamp(kps.count, max=self.topk)
         desc = torch.cat([desc_o, desc_t], 0)
-        d = pp.sample_descriptors(kps.keypoints, count, desc, H, W)
+        d = pp.sample_descriptors(kps.keypoints, count, desc, H, W, channel_last)
         m = pp.mnn_match(d[:B], d[B:], count[:B], count[B:], use_tensor_cores=self.use_tensor_cores)
         return PairResult(kps.keypoints[:B], kps.keypoints[B:], count[:B], count[B:], d[:B], d[B:], m.match_idx,
                           m.match_dist, m.count)
@@ -201,4 +263,6 @@ class PairPipeline:
     @torch.no_grad()
     def __call__(self, optical: torch.Tensor, thermal: torch.Tensor) -> PairResult:
         po, pt = self.net.forward_pair_batched(optical, thermal)
+        if po.get("desc_cl") is not None:
+            return self.tail(po["prob"], pt["prob"], po["desc_cl"], pt["desc_cl"], channel_last=True)
         return self.tail(po["prob"], pt["prob"], po["desc"], pt["desc"])

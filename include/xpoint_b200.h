@@ -190,6 +190,14 @@ XP_API int xp_patch_embed_stem(const float* img, const float* weight, const floa
                                const float* beta, void* out, int64_t B, int64_t Cin, int64_t H, int64_t W, int64_t C1,
                                float eps, int32_t out_dtype, int32_t gelu, xp_stream_t stream);
 
+/* -- f2: Linear (+ bias) (+ exact GELU) on tcgen05 tensor cores --------------------------------
+ * Replaces `fc1 -> GELU` of the VSSBlock MLP (VMamba.py:110-128, :1229-1233): out (M, N) = act(A (M, K) W (N, K)^T + bias),
+ * A / W / out in `dtype` (XP_F16 | XP_BF16), bias (N) fp32 or NULL, fp32 accumulation; gelu != 0 applies the exact (erf)
+ * GELU to the accumulator so the hidden activation is written once.  K % 8 == 0, N % 32 == 0, row-major contiguous.
+ */
+XP_API int xp_linear_act(const void* A, const void* W, const float* bias, void* out, int64_t M, int64_t N, int64_t K,
+                         int32_t dtype, int32_t gelu, xp_stream_t stream);
+
 /* -- a6: detector post ----------------------------------------------------------------
  * Replaces Softmax2d -> [:, :-1] -> PixelShuffle(r)   (XPoint.py:356-357).
  * logits (B, r*r+1, Hc, Wc) in `dtype` -> prob (B, 1, r*Hc, r*Wc) fp32.  r <= 8.

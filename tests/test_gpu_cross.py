@@ -258,3 +258,38 @@ def test_ss2d_dt_proj_vs_torch(dtype, tol, B, G, D, R, N, L):
     ref = torch.einsum("gdr,bgrl->bgdl", w, x_dbl[:, :, :R].float())
     assert out.dtype == dtype and out.shape == (B, G, D, L)
     np.testing.assert_allclose(out.float().cpu().numpy(), ref.cpu().numpy(), rtol=tol, atol=tol)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 2e-3), (torch.bfloat16, 1.6e-2)])
+@pytest.mark.parametrize("M,K,N", [(128, 96, 384), (1000, 96, 384), (20480 * 2 + 37, 96, 384), (5120, 192, 768), (640, 384, 1536),
+                                   (321, 768, 3072), (77, 16, 64), (300, 64, 320), (129, 8, 32)])
+@pytest.mark.parametrize("gelu", [True, False])
+def test_linear_act_tc_vs_torch(dtype, tol, M, K, N, gelu):
+    """fc1 (+ exact GELU) of the VSSBlock MLP (VMamba.py:110-128) on tcgen05: fp32 accumulate, 16-bit out."""
+    from xpoint_b200.cross_scan import linear_act
+    g = torch.Generator().manual_seed(M + K)
+    x = torch.randn(M, K, generator=g).to(dtype).to(DEV)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dtype).to(DEV)
+    b = (0.5 * torch.randn(N, generator=g)).to(DEV)
+    out = linear_act(x, w, b, gelu=gelu)
+    ref = x.float() @ w.float().t() + b
+    if gelu:
+        ref = torch.nn.functional.gelu(ref)
+    assert out.shape == (M, N) and out.dtype == dtype
+    np.testing.assert_allclose(out.float().cpu().numpy(), ref.cpu().numpy(), rtol=tol, atol=tol)
+
+
+def test_gelu_erf_epilogue_accuracy():
+    """The epilogue's erf (Abramowitz-Stegun 7.1.26) against torch's exact GELU on a dense sweep: identity GEMM, K = 64."""
+    from xpoint_b200.cross_scan import linear_act
+    K = 64
+    vals = torch.linspace(-8, 8, 64 * 4096)
+    # one-hot rows select fp16-representable values: out[m, n] = gelu(v[m] * [n == m % 64] ...) -> use a diagonal weight
+    x = torch.zeros(4096, K)
+    vgrid = vals.view(4096, 64)
+    w = torch.eye(64, K)
+    x[:, :64] = vgrid
+    out = linear_act(x.half().to(DEV), w.half().to(DEV), None, gelu=True).float().cpu()
+    ref = torch.nn.functional.gelu(x.half().float()[:, :64])
+    assert (out - ref).abs().max() <= 1e-3 * 8 / 8 + 2 ** -11 * ref.abs().max()   # fp16 output rounding only
+    np.testing.assert_allclose(out.numpy(), ref.half().float().numpy(), rtol=2e-3, atol=1e-4)

@@ -183,3 +183,28 @@ def patch_embed_stem(img: torch.Tensor, weight: torch.Tensor, bias, ln_weight, l
                                                       C1, float(eps), _lib.dtype_code(out), int(bool(gelu)), _lib.stream_ptr(dev)))
         _lib.count_launches(1)
     return out
+
+
+def linear_act(x: torch.Tensor, weight: torch.Tensor, bias, gelu: bool = False) -> torch.Tensor:
+    """act(x W^T + b) on tcgen05 tensor cores (xp_linear_act).  x (..., K) fp16 | bf16 contiguous, weight (N, K) in the
+    same dtype, bias (N) fp32 or None -> (..., N); gelu=True applies the exact (erf) GELU in the GEMM epilogue."""
+    dev = _lib.require_cuda(x, weight, bias)
+    if x.dtype not in (torch.float16, torch.bfloat16) or weight.dtype != x.dtype:
+        raise RuntimeError("linear_act: x and weight must both be fp16 or bf16")
+    x = x.contiguous()
+    weight = weight.contiguous()
+    N, K = weight.shape
+    if x.shape[-1] != K:
+        raise RuntimeError("linear_act: shape mismatch")
+    out = torch.empty(x.shape[:-1] + (N,), dtype=x.dtype, device=dev)
+    if out.numel():
+        b = None if bias is None else bias.float().contiguous()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().xp_linear_act(_lib.ptr(x), _lib.ptr(weight), _lib.ptr(b), _lib.ptr(out), x.numel() // K, N, K,
+                                                _lib.dtype_code(x), int(bool(gelu)), _lib.stream_ptr(dev)))
+        _lib.count_launches(1)
+    return out
+
+
+def linear_act_supported(K: int, N: int) -> bool:
+    return K % 8 == 0 and N % 32 == 0 and N <= 8192

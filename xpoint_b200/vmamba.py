@@ -21,7 +21,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ss2d as _ss2d
-from .cross_scan import add_layer_norm, cross_scan_fn, layer_norm, merge_norm_gate, patch_embed_stem
+from .cross_scan import (add_layer_norm, cross_scan_fn, layer_norm, linear_act, linear_act_supported, merge_norm_gate,
+                         patch_embed_stem)
 from .selective_scan import scan_forward, selective_scan_fn
 
 
@@ -62,6 +63,17 @@ class Mlp(nn.Module):  # VMamba.py:110-128 (channel-last only; XPoint never buil
         self.fc2 = nn.Linear(hidden_features, out_features)
 
     def forward(self, x):
+        # 16-bit activations (autocast): fc1 + bias + exact GELU in ONE tcgen05 GEMM, the hidden tensor is written once
+        if (x.is_cuda and x.dtype in (torch.float16, torch.bfloat16) and isinstance(self.act, nn.GELU)
+                and getattr(self.act, "approximate", "none") == "none"
+                and linear_act_supported(self.fc1.in_features, self.fc1.out_features) and not getattr(self, "disable_fused", False)):
+            w = self.fc1.weight
+            key = (w.data_ptr(), w._version, x.dtype)
+            cache = getattr(self, "_w1_cache", None)
+            if cache is None or cache[0] != key:
+                cache = (key, w.detach().to(x.dtype).contiguous())
+                self._w1_cache = cache
+            return self.fc2(linear_act(x, cache[1], self.fc1.bias, gelu=True))
         return self.fc2(self.act(self.fc1(x)))
 
 

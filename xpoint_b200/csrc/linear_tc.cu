@@ -12,9 +12,10 @@
 //              of two TMEM accumulators; tcgen05.commit frees the stage / publishes the accumulator
 //   warp 2     TMEM allocation (512 columns)
 //   warps 4-11 epilogue: warp e owns TMEM lane quarter e % 4 and every second 32-column chunk (e / 4): tcgen05.ld,
-//              + bias (shared memory), GELU, pack to 16 bit, four 16-byte stores per row and chunk.
-// GELU uses erf(x) = 1 - (a1 t + .. + a5 t^5) exp(-x^2), t = 1 / (1 + p x)  (Abramowitz-Stegun 7.1.26, |err| <= 1.5e-7,
-// far below the 16-bit output quantum) instead of libdevice erff: 8 epilogue warps then keep up with the store stream.
+//              + bias (shared memory), GELU, pack to 16 bit; the 32 x 32 chunk is transposed through a padded per-warp
+//              shared-memory buffer so that every store instruction writes whole 64-byte runs (8 rows x 2 sectors).
+// GELU uses erf(x) = 1 - (1 + a1 x + .. + a6 x^6)^-16 (Abramowitz-Stegun 7.1.28, |err| <= 3e-7, far below the 16-bit
+// output quantum) evaluated on packed fp32 pairs instead of libdevice erff: the epilogue keeps up with the store stream.
 #include "common.cuh"
 #include "tcgen05.cuh"
 
@@ -23,25 +24,34 @@ namespace xp {
 constexpr int LT_BM = 128, LT_BK = 64, LT_STAGES = 4;
 constexpr int LT_A_TILE = LT_BM * 128;
 constexpr int LT_EPI_WARPS = 8, LT_THREADS = (4 + LT_EPI_WARPS) * 32;
+constexpr int LT_STG_PITCH = 80, LT_STG = 32 * LT_STG_PITCH;   // per-warp transpose buffer: 32 rows x (64 B + 16 B pad)
 
 template <int BN> struct LtCfg {
     static constexpr int W_TILE = BN * 128;
     static constexpr int STAGE = LT_A_TILE + W_TILE;
-    static constexpr int SMEM_FIXED = LT_STAGES * STAGE + 1024 /*align*/ + 256 /*barriers + tmem ptr*/;
+    static constexpr int SMEM_FIXED = LT_STAGES * STAGE + 1024 /*align*/ + 256 /*barriers + tmem ptr*/ + LT_EPI_WARPS * LT_STG;
 };
 
-__device__ __forceinline__ float gelu_erf(float v) {
-    const float x = fabsf(v) * 0.70710678118654752f;
-    float t;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, x, 1.0f)));
-    float p = fmaf(t, 1.061405429f, -1.453152027f);
-    p = fmaf(t, p, 1.421413741f);
-    p = fmaf(t, p, -0.284496736f);
-    p = fmaf(t, p, 0.254829592f);
-    p *= t;
-    const float e = ex2_approx(-x * x * kLog2e);
-    const float erf_abs = fmaf(-p, e, 1.0f);                 // erf(|v| / sqrt 2)
-    return 0.5f * v + 0.5f * fabsf(v) * erf_abs;             // 0.5 v (1 + sign(v) erf|.|)
+// exact-GELU of two accumulators at once.  erf(x) = 1 - (1 + a1 x + .. + a6 x^6)^-16 for x >= 0 (Abramowitz-Stegun
+// 7.1.28, |err| <= 3e-7): one MUFU.RCP per value and otherwise only multiplies / FMAs, which issue as packed FMUL2 / FFMA2
+// (two fp32 lanes per slot) -- the epilogue warps then stay ahead of the store stream (libdevice erff is ~25 slots/value).
+__device__ __forceinline__ float2 gelu_erf2(float2 v) {
+    const float2 av = make_float2(fabsf(v.x), fabsf(v.y));
+    const float2 x = mul2(av, make_float2(0.70710678118654752f, 0.70710678118654752f));
+    float2 p = fma2(x, make_float2(0.0000430638f, 0.0000430638f), make_float2(0.0002765672f, 0.0002765672f));
+    p = fma2(p, x, make_float2(0.0001520143f, 0.0001520143f));
+    p = fma2(p, x, make_float2(0.0092705272f, 0.0092705272f));
+    p = fma2(p, x, make_float2(0.0422820123f, 0.0422820123f));
+    p = fma2(p, x, make_float2(0.0705230784f, 0.0705230784f));
+    p = fma2(p, x, make_float2(1.0f, 1.0f));
+    p = mul2(p, p); p = mul2(p, p); p = mul2(p, p); p = mul2(p, p);          // ^16
+    float2 r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(p.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(p.y));
+    // 0.5 v (1 + sign(v) erf|x|) = 0.5 v + 0.5 |v| (1 - r)
+    const float2 h = make_float2(0.5f, 0.5f);
+    const float2 t = fma2(mul2(av, make_float2(-0.5f, -0.5f)), r, mul2(av, h));   // 0.5 |v| (1 - r)
+    return fma2(v, h, t);
 }
 
 template <int BN, bool GELU, bool BF16>
@@ -57,7 +67,8 @@ linear_act_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     uint64_t* tfull = bars + 2 * LT_STAGES;        // [2]
     uint64_t* tempty = bars + 2 * LT_STAGES + 2;   // [2]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * LT_STAGES + 4);
-    float* bias_s = reinterpret_cast<float*>(base + LT_STAGES * Cfg::STAGE + 256);   // [N]
+    uint8_t* stg_all = base + LT_STAGES * Cfg::STAGE + 256;                          // [LT_EPI_WARPS][LT_STG]
+    float* bias_s = reinterpret_cast<float*>(stg_all + LT_EPI_WARPS * LT_STG);      // [N]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = (N + BN - 1) / BN;
@@ -121,10 +132,10 @@ linear_act_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     } else if (warp >= 4) {
         // ===================== epilogue: bias + GELU + store =====================
         const int e = warp - 4, q = e & 3, half = e >> 2;                    // (warp % 4) == q: the TMEM lane quarter it may read
+        uint8_t* stg = stg_all + e * LT_STG;
         for (int tl = 0; tl < ntl; ++tl) {
             const int buf = tl & 1, jt = tl % n_tiles;
-            const int row = ((int)blockIdx.x + (tl / n_tiles) * (int)gridDim.x) * LT_BM + q * 32 + lane;
-            unsigned short* orow = reinterpret_cast<unsigned short*>(out) + (int64_t)row * N;
+            const int row0 = ((int)blockIdx.x + (tl / n_tiles) * (int)gridDim.x) * LT_BM + q * 32;   // first row of this warp
             mbar_wait(&tfull[buf], (uint32_t)((tl >> 1) & 1));
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256);
@@ -137,16 +148,23 @@ linear_act_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 uint32_t pk[16];
 #pragma unroll
                 for (int t = 0; t < 32; t += 2) {
-                    float a = v[t] + bias_s[n0 + t], b = v[t + 1] + bias_s[n0 + t + 1];
-                    if (GELU) { a = gelu_erf(a); b = gelu_erf(b); }
-                    if (BF16) { const __nv_bfloat162 h = __floats2bfloat162_rn(a, b); pk[t / 2] = *reinterpret_cast<const uint32_t*>(&h); }
-                    else { const __half2 h = __floats2half2_rn(a, b); pk[t / 2] = *reinterpret_cast<const uint32_t*>(&h); }
+                    float2 ab = make_float2(v[t] + bias_s[n0 + t], v[t + 1] + bias_s[n0 + t + 1]);
+                    if (GELU) ab = gelu_erf2(ab);
+                    if (BF16) { const __nv_bfloat162 h = __floats2bfloat162_rn(ab.x, ab.y); pk[t / 2] = *reinterpret_cast<const uint32_t*>(&h); }
+                    else { const __half2 h = __floats2half2_rn(ab.x, ab.y); pk[t / 2] = *reinterpret_cast<const uint32_t*>(&h); }
                 }
-                if (row < M) {
-                    uint4* dst = reinterpret_cast<uint4*>(orow + n0);
 #pragma unroll
-                    for (int s4 = 0; s4 < 4; ++s4) dst[s4] = make_uint4(pk[4 * s4], pk[4 * s4 + 1], pk[4 * s4 + 2], pk[4 * s4 + 3]);
+                for (int s4 = 0; s4 < 4; ++s4)
+                    *reinterpret_cast<uint4*>(stg + lane * LT_STG_PITCH + s4 * 16) = make_uint4(pk[4 * s4], pk[4 * s4 + 1], pk[4 * s4 + 2], pk[4 * s4 + 3]);
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {                                  // lane -> (row lane/4 + 8 i, 16-byte piece lane % 4)
+                    const int r = (lane >> 2) + 8 * i, piece = lane & 3;
+                    const uint4 val = *reinterpret_cast<const uint4*>(stg + r * LT_STG_PITCH + piece * 16);
+                    if (row0 + r < M)
+                        *reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(out) + (int64_t)(row0 + r) * N + n0 + piece * 8) = val;
                 }
+                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();

@@ -172,6 +172,22 @@ __device__ __forceinline__ float softplus_f(float x) {
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
+// exact (erf) GELU with erf(x) = 1 - (1 + a1 x + .. + a6 x^6)^-16, x >= 0 (Abramowitz-Stegun 7.1.28, |err| <= 3e-7):
+// one MUFU.RCP and 13 FP32 ops instead of libdevice erff's ~25 instructions and branches.
+__device__ __forceinline__ float gelu_erf_f(float v) {
+    const float av = fabsf(v), x = av * 0.70710678118654752f;
+    float p = fmaf(x, 0.0000430638f, 0.0002765672f);
+    p = fmaf(p, x, 0.0001520143f);
+    p = fmaf(p, x, 0.0092705272f);
+    p = fmaf(p, x, 0.0422820123f);
+    p = fmaf(p, x, 0.0705230784f);
+    p = fmaf(p, x, 1.0f);
+    p *= p; p *= p; p *= p; p *= p;
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p));
+    return fmaf(v, 0.5f, fmaf(-0.5f * av, r, 0.5f * av));      // 0.5 v + 0.5 |v| (1 - r)
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(128) patch_embed_stem_kernel(const float* __re
     for (int c = 0; c < STEM_MAXC; ++c) {
         if (c < C1) {
             float v = fmaf(acc[c] * rstd, sg[c], sbe[c]);
-            if (gelu) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));     // exact (erf) GELU, nn.GELU default
+            if (gelu) v = gelu_erf_f(v);                                     // exact (erf) GELU, nn.GELU default
             acc[c] = v;
         }
     }

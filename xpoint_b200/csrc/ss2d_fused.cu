@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(256) ss2d_dt_proj_kernel(const T* __restrict__
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
             if (r < R) {
-                const float w = __ldg(Wg + (int64_t)d * R + r);
+                const float w = __ldg(Wg + (int64_t)d * R + r);     // the warp shares the row: one broadcast L1 hit
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) acc[j] = fmaf(w, x[r][j], acc[j]);
             }
@@ -423,8 +423,12 @@ static int merge_norm_launch(const float* ys, const float* gamma, const float* b
 template <typename TO>
 static int merge_norm_dispatch(const float* ys, const float* gamma, const float* beta, const void* zact, void* out, int64_t B,
                                int64_t D, int64_t H, int64_t W, float eps, cudaStream_t st) {
-    // 8x8 tokens while the fp32 tile fits comfortably (two CTAs per SM up to D = 384), 4x8 / 4x4 for wide blocks
-    if (D <= 768) return merge_norm_launch<TO, 8, 8>(ys, gamma, beta, zact, out, B, D, H, W, eps, st);
+    // 8x8 tokens for narrow blocks (25 KiB tile, 8 CTAs / SM at D = 96); from D = 192 on the 4x8 tile wins because it
+    // doubles the resident CTAs (measured on B200: D = 192 1.01 -> 0.58 ms, D = 768 0.26 -> 0.18 ms); 4x4 for very wide blocks
+    static const int tile_env = getenv("XP_MN_TILE") ? atoi(getenv("XP_MN_TILE")) : 0;     // tuning knob: 48 = 4x8, 44 = 4x4
+    if (tile_env == 48 && D <= 1536) return merge_norm_launch<TO, 4, 8>(ys, gamma, beta, zact, out, B, D, H, W, eps, st);
+    if (tile_env == 44) return merge_norm_launch<TO, 4, 4>(ys, gamma, beta, zact, out, B, D, H, W, eps, st);
+    if (D <= 128) return merge_norm_launch<TO, 8, 8>(ys, gamma, beta, zact, out, B, D, H, W, eps, st);
     if (D <= 1536) return merge_norm_launch<TO, 4, 8>(ys, gamma, beta, zact, out, B, D, H, W, eps, st);
     return merge_norm_launch<TO, 4, 4>(ys, gamma, beta, zact, out, B, D, H, W, eps, st);
 }

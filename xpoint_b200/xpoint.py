@@ -171,15 +171,27 @@ class XPoint(nn.Module):
         return folded
 
     def _heads_fused(self, x):
-        f = self._folded_heads()
+        f32w = self._folded_heads()
         cdt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
+        f = f32w.get(cdt)
+        if f is None:                            # weights cast once per compute dtype
+            f = {k: (v.to(cdt) if torch.is_tensor(v) else v) for k, v in f32w.items() if not isinstance(k, torch.dtype)}
+            f["w1"] = f["w1"].contiguous(memory_format=torch.channels_last)
+            f32w[cdt] = f
         Bn, _, Hc, Wc = x.shape
         xp = self.detector_head_convolutions[0](x).to(dtype=cdt, memory_format=torch.channels_last)   # pad once for both heads
-        y = nn.functional.conv2d(xp, f["w1"].to(cdt)).permute(0, 2, 3, 1)                            # (B, Hc, Wc, 512)
-        y = torch.relu_(y + f["b1"].to(cdt)).reshape(-1, y.shape[-1])
+        y = None
+        if not getattr(self, "_no_cudnn_relu", False):
+            try:                                 # cuDNN's fused conv + bias + ReLU
+                y = torch.cudnn_convolution_relu(xp, f["w1"], f["b1"], (1, 1), (0, 0), (1, 1), 1)
+            except RuntimeError:
+                self._no_cudnn_relu = True
+        if y is None:
+            y = torch.relu_(nn.functional.conv2d(xp, f["w1"], f["b1"]))
+        y = y.permute(0, 2, 3, 1).reshape(-1, y.shape[1])                                            # (rows, 512) channel-last
         n1 = f["n1"]
-        logits = torch.addmm(f["b2_det"].to(cdt), y[:, :n1], f["w2_det"].to(cdt))                   # (rows, 65)
-        draw = torch.addmm(f["b2_desc"].to(cdt), y[:, n1:], f["w2_desc"].to(cdt))                   # (rows, 256)
+        logits = torch.addmm(f["b2_det"], y[:, :n1], f["w2_det"])                                    # (rows, 65)
+        draw = torch.addmm(f["b2_desc"], y[:, n1:], f["w2_desc"])                                    # (rows, 256)
         logits = logits.view(Bn, Hc, Wc, -1).permute(0, 3, 1, 2).contiguous()
         draw = draw.view(Bn, Hc, Wc, -1).permute(0, 3, 1, 2).contiguous()
         if self.config["force_return_logits"]:

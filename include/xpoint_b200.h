@@ -221,7 +221,7 @@ XP_API int xp_l2_normalize(const void* x, float* out_cf, float* out_cl, int64_t 
  * keypoints (B, kp_capacity, 2) int32 (y, x) in raster order and kp_count (B) int32 are optional
  * (nullable); pixels counted are those with prob_nms > kp_threshold; kp_count holds the true count even
  * if it exceeds kp_capacity (only the first kp_capacity are written).
- * workspace: xp_nms_workspace_bytes(B, H, W) bytes of device memory.
+ * workspace: xp_nms_workspace_bytes(B, H, W) bytes of device memory, 16-byte aligned (state + scan-cursor byte planes).
  */
 XP_API int64_t xp_nms_workspace_bytes(int64_t B, int64_t H, int64_t W);
 XP_API int xp_box_nms(const float* prob, float* prob_nms, int64_t B, int64_t H, int64_t W, float size, float min_prob,

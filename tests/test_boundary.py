@@ -69,7 +69,7 @@ def test_validation_errors_without_gpu():
     with pytest.raises(NotImplementedError):
         _lib.check(lib.xp_selective_scan_bwd())
     assert lib.xp_box_nms(None, None, 1, 4, 4, 8.0, 0.1, 0.1, 0, 0.0, None, None, 0, None, 0, None) == _lib.XP_ERR_INVALID_ARG
-    assert lib.xp_nms_workspace_bytes(2, 10, 10) == 200
+    assert lib.xp_nms_workspace_bytes(2, 10, 10) == 400      # state + scan-cursor byte planes
     assert lib.xp_mnn_match(16, 16, None, None, 1, 8, 8, 256, None, None, None, None, None, 1, None, 0, None) == _lib.XP_ERR_WORKSPACE
 
 

@@ -5,6 +5,8 @@
 //   bilinear descriptor sampling + L2 norm (xpoint/utils/utils.py:229-238)
 // All kernels are HBM/L2-bound integer/byte/fp32 work: coalesced 128-byte rows, warp shuffles and ballots,
 // no tensor cores.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace xp {
@@ -441,7 +443,14 @@ extern "C" int xp_l2_normalize(const void* x, float* out_cf, float* out_cl, int6
     }
 }
 
-extern "C" int64_t xp_nms_workspace_bytes(int64_t B, int64_t H, int64_t W) { return B * H * W; }
+namespace xp {
+int launch_box_nms_fast(const float* prob, float* prob_nms, int64_t B, int64_t H, int64_t W, float size, float min_prob, float iou,
+                        int64_t keep_top_k, float kp_threshold, int32_t* keypoints, int32_t* kp_count, int64_t kp_capacity,
+                        void* workspace, cudaStream_t st);
+}
+
+// state bytes + scan-cursor bytes (nms_fast.cu)
+extern "C" int64_t xp_nms_workspace_bytes(int64_t B, int64_t H, int64_t W) { return 2 * B * H * W; }
 
 extern "C" int xp_box_nms(const float* prob, float* prob_nms, int64_t B, int64_t H, int64_t W, float size, float min_prob,
                           float iou, int64_t keep_top_k, float kp_threshold, int32_t* keypoints, int32_t* kp_count,
@@ -458,6 +467,14 @@ extern "C" int xp_box_nms(const float* prob, float* prob_nms, int64_t B, int64_t
         return XP_ERR_WORKSPACE;
     }
     if (B == 0) return XP_OK;
+    {   // widths that are multiples of 8 (every XPoint input size) take the vectorised kernel (nms_fast.cu)
+        const uintptr_t al = reinterpret_cast<uintptr_t>(prob) | reinterpret_cast<uintptr_t>(workspace) |
+                             reinterpret_cast<uintptr_t>(prob_nms);
+        static const bool no_fast = getenv("XP_NMS_GENERIC") != nullptr;      // testing knob
+        if (W % 8 == 0 && (al & 15) == 0 && !no_fast && size <= 8.0f)      // <= 224 footprint offsets: one-byte cursors
+            return xp::launch_box_nms_fast(prob, prob_nms, B, H, W, size, min_prob, iou, keep_top_k, kp_threshold, keypoints,
+                                           kp_count, kp_capacity, workspace, (cudaStream_t)stream);
+    }
     NmsParams p;
     p.prob = prob; p.out = prob_nms; p.state = (uint8_t*)workspace; p.kp = keypoints; p.kp_count = kp_count;
     p.H = (int)H; p.W = (int)W; p.size = size; p.min_prob = min_prob; p.iou = iou; p.kp_thr = kp_threshold;

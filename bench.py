@@ -247,7 +247,7 @@ def run_ours(args):
     scan_bytes = sum(n for _, _, n, _ in prof)
     by_shape = {}
     for a, b, n, shp in prof:
-        k = "B{} KD{} K{} N{} L{} {}->{}".format(*shp).replace("torch.", "")
+        k = "B{} KD{} K{} N{} L{} {}->{}".format(*shp[:7]).replace("torch.", "") + (f" fused-dt R{shp[7]}" if shp[7] else "")
         s = by_shape.setdefault(k, [0, 0.0, 0])
         s[0] += 1
         s[1] += a.elapsed_time(b)

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define XP_ABI_VERSION 2
+#define XP_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define XP_API __attribute__((visibility("default")))
@@ -71,6 +71,14 @@ XP_API int xp_check_device(void);
  * Bit g of reverse_group_mask makes group g (g < 64) walk the sequence backwards through memory: every
  * per-token tensor of that group (u, delta, B, C, z) is read at token L-1-l at scan step l and out is written
  * there, i.e. its y stays in natural (unflipped) memory order (CrossMerge's flips, csm_triton.py:56-62).
+ *
+ * Fused dt_proj (ABI 3; SURVEY 8f row f1 -- VMamba.py:605-615 computes delta = dt_projs_weight x dts_r and hands the
+ * materialised (batch, dim, seqlen) tensor to the scan).  With dt_rank > 0 the scan takes the low-rank factors instead
+ * and the (batch, dim, seqlen) delta never exists in HBM: `delta` points at dts_r (batch, groups, dt_rank, seqlen) in
+ * in_dtype with element strides delta_batch_stride / dt_group_stride / delta_dim_stride (= rank-row stride), dt_weight is
+ * (dim, dt_rank) contiguous in in_dtype, and
+ *     delta_l[d] = sum_r dt_weight[d, r] * dts_r[b, g(d), r, l]        (exact products, fp32 accumulation, r ascending)
+ * before delta_bias / softplus.  delta_dim must equal dim.  dt_rank <= 64.
  */
 typedef struct {
     const void* u;
@@ -98,6 +106,10 @@ typedef struct {
     int64_t u_group_stride;       /* elements */
     int64_t u_group_div;          /* 0 = classic addressing */
     uint64_t reverse_group_mask;  /* bit g = group g runs backwards through memory */
+    /* fused dt_proj, see above (all zero = delta is materialised) */
+    const void* dt_weight;        /* (dim, dt_rank) in_dtype, contiguous */
+    int64_t dt_rank;
+    int64_t dt_group_stride;      /* elements */
 } xp_scan_args;
 
 XP_API int xp_selective_scan_fwd(const xp_scan_args* args, xp_stream_t stream);

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(handle, s), f"{s} declared in include/xpoint_b200.h but not exported"
     assert sorted(_lib.exported_symbols()) == syms, "ctypes signature table out of sync with the header"
-    assert _lib.lib().xp_abi_version() == 2
+    assert _lib.lib().xp_abi_version() == 3
 
 
 def test_header_compiles_as_plain_c(tmp_path):
@@ -47,7 +47,7 @@ def test_scan_args_struct_layout_matches_header():
         _, rest = decl.split(None, 1)
         names += [n.strip().lstrip("*") for n in rest.split(",")]
     assert names == [f[0] for f in _lib.ScanArgs._fields_]
-    assert ctypes.sizeof(_lib.ScanArgs) == 10 * 8 + 20 * 8 + 4 * 4 + 3 * 8
+    assert ctypes.sizeof(_lib.ScanArgs) == 10 * 8 + 20 * 8 + 4 * 4 + 3 * 8 + 3 * 8
 
 
 def test_validation_errors_without_gpu():

@@ -70,6 +70,22 @@ def test_ss2d_fused_matches_unfused(dtype, ft, N, ratio):
     assert_close(y.float().cpu().numpy(), yu.float().cpu().numpy(), 2e-5 if dtype == torch.float32 else 1e-2, f"{ft} {dtype}")
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("C", [96, 192, 384])
+def test_ss2d_fused_dt_proj_matches_materialised_delta(dtype, C):
+    """dt ranks 6 / 12 form delta inside the scan (xp_scan_args.dt_weight), rank 24 keeps the
+    materialised delta; both must agree with the dt_proj -> scan path of the same module."""
+    import xpoint_b200 as X
+    torch.manual_seed(1)
+    m = X.SS2D(d_model=C, d_state=1, ssm_ratio=1.0, forward_type="v05_noz", conv_bias=False).to(DEV).eval()
+    x = torch.randn(2, 32, 40, C, device=DEV)
+    with torch.no_grad(), torch.autocast("cuda", dtype=dtype, enabled=dtype != torch.float32):
+        y = m(x)
+        m.disable_dt_fusion = True
+        ym = m(x)
+    assert_close(y.float().cpu().numpy(), ym.float().cpu().numpy(), 2e-5 if dtype == torch.float32 else 1e-2, f"C={C} {dtype}")
+
+
 @pytest.mark.parametrize("H,W,C", [(128, 160, 96), (64, 80, 192), (32, 40, 384), (16, 20, 768)])
 def test_ss2d_fp16_autocast_at_xpoint_stage_shapes(H, W, C):
     """The four stage shapes of preset E at 512x640: fp16 autocast (the reference's

@@ -163,6 +163,66 @@ def test_fused_cross_scan_addressing(dtype, N, L, use_z):
         assert_close(last.cpu().numpy(), rlast, tol, "fused addressing last state")
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("N,R,L", [(1, 6, 5120), (1, 12, 1280), (1, 6, 328), (1, 7, 2056), (2, 16, 776), (1, 1, 64), (1, 3, 24),
+                                   (1, 24, 320), (16, 6, 512), (4, 5, 100)])
+@pytest.mark.parametrize("addressing", ["plain", "ss2d"])
+def test_fused_dt_proj(dtype, N, R, L, addressing):
+    """xp_scan_args.dt_weight / dt_rank (ABI 3): the scan forms delta = dt_projs_weight x dts_r itself
+    (VMamba.py:605-615) from a strided view of the x_proj output.  The oracle gets the materialised fp32 delta.  Ranks
+    <= 16 with N <= 2 run on the lanes kernel (FHFMA for 16-bit inputs), everything else on the generic kernel; "ss2d"
+    adds the shared-u / reversed-group addressing of the copy-free SS2D path."""
+    X, O = _imports()
+    from xpoint_b200.selective_scan import scan_forward
+    Bt, K, Dg = 2, 4, 24
+    u, _, A, _, _, D, _, bias = make_inputs(L + 5 * N + R, Bt, K * Dg, K, N, L, dtype=dtype)
+    g = torch.Generator().manual_seed(R)
+    x_dbl = torch.randn(Bt, K, R + 2 * N, L, generator=g).to(dtype)        # the fused x_proj output (VMamba.py:606)
+    x_dbl[:, :, :R] *= 0.3
+    wdt = (torch.randn(K * Dg, R, generator=g) * R ** -0.5).to(dtype)
+    dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
+    delta = torch.from_numpy(O.dt_proj(dts, wdt))
+    div, mask = (2, 0b1010) if addressing == "ss2d" else (1, 0)
+    rev = [bool((mask >> k) & 1) for k in range(K)]
+    usrc = u[:, : (K // div) * Dg].contiguous()
+    ufull = torch.cat([usrc[:, (k // div) * Dg:(k // div + 1) * Dg] for k in range(K)], dim=1)
+
+    def flip(t, groups_dim_rows):       # flip the reversed groups along L
+        t = t.clone().float()
+        v = t.view(Bt, K, -1, L)
+        for k in range(K):
+            if rev[k]:
+                v[:, k] = v[:, k].flip(-1)
+        return t
+
+    ref, rlast = O.selective_scan(flip(ufull, True), flip(delta, True), A, flip(Bs.contiguous(), False), flip(Cs.contiguous(), False),
+                                  D, None, bias, True, return_last_state=True)
+    ref = flip(torch.from_numpy(np.ascontiguousarray(ref)), True).numpy()
+    xd = x_dbl.to(DEV)
+    dts_d, Bs_d, Cs_d = torch.split(xd, [R, N, N], dim=2)
+    for force_generic in (False, True):
+        out, last = scan_forward(usrc.to(DEV), dts_d, A.to(DEV), Bs_d, Cs_d, D.to(DEV), None, bias.to(DEV), True, True, True,
+                                 force_generic=force_generic, u_group_div=div, reverse_group_mask=mask, dt_weight=wdt.to(DEV))
+        # identical pre-rounded factors on both sides and fp32 accumulation: the fp32 bar holds for 16-bit inputs too
+        assert_close(out.cpu().numpy(), ref, FP32_REL, f"fused dt_proj {dtype} N={N} R={R} L={L} generic={force_generic}")
+        assert_close(last.cpu().numpy(), rlast, FP32_REL, "fused dt_proj last state")
+
+
+def test_fused_dt_proj_errors():
+    X, _ = _imports()
+    from xpoint_b200.selective_scan import scan_forward
+    u, dl, A, B, C, D, z, bias = cu(*make_inputs(0, 2, 8, 2, 1, 16))
+    dts = torch.randn(2, 2, 3, 16, device=DEV)
+    w = torch.randn(8, 3, device=DEV)
+    assert scan_forward(u, dts, A, B, C, D, None, bias, True, dt_weight=w)[0].shape == (2, 8, 16)
+    with pytest.raises(RuntimeError):
+        scan_forward(u, dts, A, B, C, D, None, bias, True, dt_weight=w[:, :2])       # rank mismatch
+    with pytest.raises(RuntimeError):
+        scan_forward(u, dts[:, :1], A, B, C, D, None, bias, True, dt_weight=w)       # groups mismatch
+    with pytest.raises(RuntimeError):
+        scan_forward(u, dts, A, B, C, D, None, bias, True, dt_weight=w.half())       # dtype mismatch
+
+
 def test_delta_groups_and_strided_views():
     X, O = _imports()
     u, dl, A, B, C, D, z, bias = make_inputs(5, 2, 24, 2, 4, 96, KD1=6)

@@ -32,6 +32,7 @@ class ScanArgs(Structure):
                                   "z_batch_stride", "z_dim_stride", "out_batch_stride", "out_dim_stride")]
         + [(n, c_int32) for n in ("in_dtype", "out_dtype", "delta_softplus", "force_generic")]
         + [("u_group_stride", c_int64), ("u_group_div", c_int64), ("reverse_group_mask", ctypes.c_uint64)]
+        + [("dt_weight", c_void_p), ("dt_rank", c_int64), ("dt_group_stride", c_int64)]
     )
 
 
@@ -96,7 +97,7 @@ def lib() -> ctypes.CDLL:
             fn = getattr(handle, name)  # raises AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if handle.xp_abi_version() != 2:
+        if handle.xp_abi_version() != 3:
             raise RuntimeError("libxpoint_b200.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -35,6 +35,8 @@ struct ScanParams {
     int64_t u_bs, u_ds, dl_bs, dl_ds, B_bs, B_gs, B_ss, C_bs, C_gs, C_ss, z_bs, z_ds, o_bs, o_ds;
     int64_t u_gs, u_gdiv;   // u row of (b, g, dg) = u + b*u_bs + (g / u_gdiv)*u_gs + dg*u_ds
     uint64_t rev_mask;      // bit g: group g walks memory backwards (all tensors, including out)
+    const void* wdt;        // fused dt_proj: (dim, R) weights in IN_T; delta then points at dts_r (batch, groups, R, L)
+    int64_t R, dl_gs;       //   rank (0 = delta is materialised), group stride of dts_r (dl_ds = its rank-row stride)
     int softplus;
     int rows_per_warp;   // scan_lanes only
 };
@@ -42,6 +44,28 @@ struct ScanParams {
 __device__ __forceinline__ float delta_act(float d, float bias, int softplus) {
     d += bias;
     return softplus ? softplus_f(d) : d;
+}
+
+// acc + a*b with 16-bit a, b and an fp32 accumulator in ONE instruction (FHFMA, sm_100 mixed-precision fma): the product
+// of two 16-bit floats is exact in fp32, so this equals fmaf(float(a), float(b), acc).
+template <typename IN_T> __device__ __forceinline__ float fma_mixed(unsigned short a, unsigned short b, float acc);
+template <> __device__ __forceinline__ float fma_mixed<__half>(unsigned short a, unsigned short b, float acc) {
+    float d;
+    asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"(a), "h"(b), "f"(acc));
+    return d;
+}
+template <> __device__ __forceinline__ float fma_mixed<__nv_bfloat16>(unsigned short a, unsigned short b, float acc) {
+    float d;
+    asm("fma.rn.f32.bf16 %0, %1, %2, %3;" : "=f"(d) : "h"(a), "h"(b), "f"(acc));
+    return d;
+}
+
+// delta of one token from the low-rank factors (fused dt_proj): sum_r w[r] * x[r*xs + l], r ascending, fp32 accumulation
+template <typename IN_T>
+__device__ __forceinline__ float delta_lowrank(const IN_T* x, int64_t xs, const IN_T* w, int R, int64_t l) {
+    float acc = 0.0f;
+    for (int r = 0; r < R; ++r) acc = fmaf(to_f32(w[r]), to_f32(x[r * xs + l]), acc);
+    return acc;
 }
 
 // ============================================================================================
@@ -63,7 +87,9 @@ __global__ void __launch_bounds__(GEN_WARPS * 32) scan_generic_kernel(const Scan
     const int64_t Dg = p.dim / p.groups;
     const bool rev = g < 64 && ((p.rev_mask >> g) & 1);
     const IN_T* u = (const IN_T*)p.u + b * p.u_bs + (g / p.u_gdiv) * p.u_gs + (d - g * Dg) * p.u_ds;
-    const IN_T* dl = (const IN_T*)p.delta + b * p.dl_bs + dd * p.dl_ds;
+    const int R = (int)p.R;
+    const IN_T* dl = R ? (const IN_T*)p.delta + b * p.dl_bs + g * p.dl_gs : (const IN_T*)p.delta + b * p.dl_bs + dd * p.dl_ds;
+    const IN_T* wdt = R ? (const IN_T*)p.wdt + d * R : nullptr;
     const IN_T* Bm = (const IN_T*)p.Bm + b * p.B_bs + g * p.B_gs;
     const IN_T* Cm = (const IN_T*)p.Cm + b * p.C_bs + g * p.C_gs;
     const IN_T* z = p.z ? (const IN_T*)p.z + b * p.z_bs + d * p.z_ds : nullptr;
@@ -83,7 +109,8 @@ __global__ void __launch_bounds__(GEN_WARPS * 32) scan_generic_kernel(const Scan
         for (int j = 0; j < GEN_C; ++j) {
             const bool ok = l0 + j < p.L;
             uv[j] = ok ? to_f32(u[mem(l0 + j)]) : 0.0f;
-            dv[j] = ok ? delta_act(to_f32(dl[mem(l0 + j)]), bias, p.softplus) : 0.0f;  // 0 -> identity step
+            const float draw = !ok ? 0.0f : R ? delta_lowrank(dl, p.dl_ds, wdt, R, mem(l0 + j)) : to_f32(dl[mem(l0 + j)]);
+            dv[j] = ok ? delta_act(draw, bias, p.softplus) : 0.0f;                       // 0 -> identity step
             y[j] = Dv * uv[j];
         }
         for (int n = 0; n < N; ++n) {
@@ -204,16 +231,26 @@ __device__ __forceinline__ void store_tokens(OUT_T* gp, const float (&y)[C], int
     }
 }
 
-template <int NST, typename IN_T, int C, bool HAS_Z, int NW> struct LanesCfg {
+template <int NST, typename IN_T, int C, bool HAS_Z, int NW, bool DTF> struct LanesCfg {
     static constexpr int TOK = 32 * C;                                   // tokens per step
     static constexpr int CHUNK = TOK * (int)sizeof(IN_T);                // bytes of one row chunk
-    static constexpr int ITEM = CHUNK * (HAS_Z ? 3 : 2);                 // u, delta [, z]
-    static constexpr int BC = 2 * NST * CHUNK;                           // B rows then C rows
-    static constexpr int RCF = NST == 1 ? 4 : 8;                         // floats of per-row constants
-    static constexpr int RC_BYTES = LN_MAXROWS * RCF * 4;
-    static constexpr int WARP_BYTES = LN_STAGES * ITEM + LN_BCS * BC + RC_BYTES;
-    static constexpr int NBARS = 2 * LN_STAGES + 2 * LN_BCS;             // full/empty + bcfull/bcempty
-    static constexpr int SMEM = NW * (WARP_BYTES + NBARS * 8) + 16;
+    static constexpr int ITEM = CHUNK * ((HAS_Z ? 2 : 1) + (DTF ? 0 : 1));   // u [, delta] [, z]
+    static constexpr int ZOFF = CHUNK * (DTF ? 1 : 2);
+    static constexpr int RCF = NST == 1 ? 4 : 8;                         // floats of per-row scalar constants
+    // fused dt_proj with 512-token steps: the R rank rows dominate shared memory; a 2-deep u ring keeps 3 CTAs per SM
+    static constexpr int STAGES = (DTF && C == 16) ? 2 : LN_STAGES;
+    static constexpr int NBARS = 2 * STAGES + 2 * LN_BCS;                // full/empty + bcfull/bcempty
+    // The rest depends on the dt rank R of the fused dt_proj (R = 0 unless DTF: everything folds to constants).
+    //   aux buffer: B rows, C rows, then the R rows of dts_r; row table: RCF scalars + the row's dt weights
+    __host__ __device__ static constexpr int aux(int R) { return (2 * NST + (DTF ? R : 0)) * CHUNK; }
+    __host__ __device__ static constexpr int wwords(int R) {
+        return DTF ? ((((int)sizeof(IN_T) == 2 ? (R + 1) / 2 : R) + 3) & ~3) : 0;
+    }
+    __host__ __device__ static constexpr int rcw(int R) { return RCF + wwords(R); }
+    __host__ __device__ static constexpr int warp_bytes(int R) {
+        return STAGES * ITEM + LN_BCS * aux(R) + LN_MAXROWS * rcw(R) * 4;
+    }
+    __host__ __device__ static constexpr int smem(int R) { return NW * (warp_bytes(R) + NBARS * 8) + 16; }
 };
 
 struct LanesWarp {   // decoded work assignment of one consumer warp
@@ -235,24 +272,27 @@ __device__ __forceinline__ LanesWarp lanes_decode(const ScanParams& p, int64_t w
     return w;
 }
 
-template <int NST, typename IN_T, int C, bool HAS_Z, int NW>
+template <int NST, typename IN_T, int C, bool HAS_Z, int NW, bool DTF>
 __device__ __forceinline__ void lanes_producer(const ScanParams& p, uint8_t* base, int lane) {
-    using Cfg = LanesCfg<NST, IN_T, C, HAS_Z, NW>;
+    using Cfg = LanesCfg<NST, IN_T, C, HAS_Z, NW, DTF>;
     constexpr int TOK = Cfg::TOK;
     constexpr int ES = (int)sizeof(IN_T);
+    const int R = DTF ? (int)p.R : 0;
+    const int WB = Cfg::warp_bytes(R), AUX = Cfg::aux(R);
     const bool mine = lane < NW;
     const LanesWarp w = lanes_decode(p, (int64_t)blockIdx.x * NW + (mine ? lane : 0));
-    uint8_t* ring = base + (mine ? lane : 0) * Cfg::WARP_BYTES;
-    uint8_t* bcbuf = ring + LN_STAGES * Cfg::ITEM;
-    uint64_t* full = reinterpret_cast<uint64_t*>(base + NW * Cfg::WARP_BYTES) + (mine ? lane : 0) * Cfg::NBARS;
-    uint64_t* empty = full + LN_STAGES;
-    uint64_t* bcfull = empty + LN_STAGES;
+    uint8_t* ring = base + (mine ? lane : 0) * WB;
+    uint8_t* bcbuf = ring + Cfg::STAGES * Cfg::ITEM;
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + NW * WB) + (mine ? lane : 0) * Cfg::NBARS;
+    uint64_t* empty = full + Cfg::STAGES;
+    uint64_t* bcfull = empty + Cfg::STAGES;
     uint64_t* bcempty = bcfull + LN_BCS;
     const int64_t Dg = p.dim / p.groups;
     const int64_t dg0 = w.d0 - w.g * Dg;
     const bool rev = (p.rev_mask >> (w.g & 63)) & 1 && w.g < 64;
     const IN_T* ub = (const IN_T*)p.u + w.b * p.u_bs + (w.g / p.u_gdiv) * p.u_gs + dg0 * p.u_ds;
-    const IN_T* db = (const IN_T*)p.delta + w.b * p.dl_bs + w.d0 * p.dl_ds;
+    // materialised delta: the warp's first row; fused dt_proj: the R rank rows of the warp's (batch, group)
+    const IN_T* db = DTF ? (const IN_T*)p.delta + w.b * p.dl_bs + w.g * p.dl_gs : (const IN_T*)p.delta + w.b * p.dl_bs + w.d0 * p.dl_ds;
     const IN_T* zb = HAS_Z ? (const IN_T*)p.z + w.b * p.z_bs + w.d0 * p.z_ds : nullptr;
     const IN_T* Bb = (const IN_T*)p.Bm + w.b * p.B_bs + w.g * p.B_gs;
     const IN_T* Cb = (const IN_T*)p.Cm + w.b * p.C_bs + w.g * p.C_gs;
@@ -275,21 +315,26 @@ __device__ __forceinline__ void lanes_producer(const ScanParams& p, uint8_t* bas
                 const uint32_t off = rev ? (uint32_t)((TOK - valid) * ES) : 0u; // mirrored windows are right-aligned
                 const uint32_t bytes = (uint32_t)(valid * ES);
                 uint8_t* dst = ring + slot * Cfg::ITEM + off;
-                mbar_arrive_expect_tx(&full[slot], bytes * (HAS_Z ? 3 : 2));
+                mbar_arrive_expect_tx(&full[slot], bytes * (Cfg::ITEM / Cfg::CHUNK));
                 bulk_load(dst, ub + r * p.u_ds + m0, bytes, &full[slot]);
-                bulk_load(dst + Cfg::CHUNK, db + r * p.dl_ds + m0, bytes, &full[slot]);
-                if (HAS_Z) bulk_load(dst + 2 * Cfg::CHUNK, zb + r * p.z_ds + m0, bytes, &full[slot]);
+                if (!DTF) bulk_load(dst + Cfg::CHUNK, db + r * p.dl_ds + m0, bytes, &full[slot]);
+                if (HAS_Z) bulk_load(dst + Cfg::ZOFF, zb + r * p.z_ds + m0, bytes, &full[slot]);
                 if (r == 0) {
-                    uint8_t* bc = bcbuf + bs * Cfg::BC + off;
-                    mbar_arrive_expect_tx(&bcfull[bs], bytes * 2 * NST);
+                    uint8_t* bc = bcbuf + bs * AUX + off;
+                    mbar_arrive_expect_tx(&bcfull[bs], bytes * (2 * NST + R));
 #pragma unroll
                     for (int n = 0; n < NST; ++n) {
                         bulk_load(bc + n * Cfg::CHUNK, Bb + n * p.B_ss + m0, bytes, &bcfull[bs]);
                         bulk_load(bc + (NST + n) * Cfg::CHUNK, Cb + n * p.C_ss + m0, bytes, &bcfull[bs]);
                     }
+                    if (DTF) {
+#pragma unroll 1
+                        for (int q = 0; q < R; ++q)
+                            bulk_load(bc + (2 * NST + q) * Cfg::CHUNK, db + q * p.dl_ds + m0, bytes, &bcfull[bs]);
+                    }
                 }
                 if (++r == w.nrows) { r = 0; ++step; }
-                if (++slot == LN_STAGES) { slot = 0; ++fill; }
+                if (++slot == Cfg::STAGES) { slot = 0; ++fill; }
                 ++it;
                 issued = true;
             }
@@ -298,24 +343,66 @@ __device__ __forceinline__ void lanes_producer(const ScanParams& p, uint8_t* bas
     }
 }
 
-template <int NST, typename IN_T, typename OUT_T, int C, bool HAS_Z, bool SOFTPLUS, bool REV, int NW>
+// dv[j] += w * x[j] for the C tokens of this lane, x read from shared memory (one dts_r rank row), REV mirrors the order.
+// 16-bit: the raw packed halves feed FHFMA directly (no widening); `w` holds the weight in the low 16 bits.
+template <typename IN_T, int C, bool REV>
+__device__ __forceinline__ void dt_accumulate(uint32_t saddr, uint32_t w, float (&dv)[C]) {
+    if constexpr (sizeof(IN_T) == 2) {
+#pragma unroll
+        for (int v = 0; v < C / 8; ++v) {
+            const uint4 q = lds128(saddr + 16 * v);
+            const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int m = v * 8 + 2 * k;
+                float& lo = dv[REV ? C - 1 - m : m];
+                float& hi = dv[REV ? C - 2 - m : m + 1];
+                lo = fma_mixed<IN_T>((unsigned short)(qq[k] & 0xffffu), (unsigned short)w, lo);
+                hi = fma_mixed<IN_T>((unsigned short)(qq[k] >> 16), (unsigned short)w, hi);
+            }
+        }
+    } else {
+        const float wf = __uint_as_float(w);
+#pragma unroll
+        for (int v = 0; v < C / 4; ++v) {
+            const uint4 q = lds128(saddr + 16 * v);
+            const float x[4] = {__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w)};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float& d = dv[REV ? C - 1 - (v * 4 + k) : v * 4 + k];
+                d = fmaf(wf, x[k], d);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
+template <int NST, typename IN_T, typename OUT_T, int C, bool HAS_Z, bool SOFTPLUS, bool REV, int NW, bool DTF>
 __device__ __forceinline__ void lanes_consumer(const ScanParams& p, uint8_t* base, const LanesWarp& w, int warp, int lane) {
-    using Cfg = LanesCfg<NST, IN_T, C, HAS_Z, NW>;
+    using Cfg = LanesCfg<NST, IN_T, C, HAS_Z, NW, DTF>;
     constexpr int TOK = Cfg::TOK, RCF = Cfg::RCF;
     constexpr bool FAST = SOFTPLUS && sizeof(IN_T) == 2;
+    const int R = DTF ? (int)p.R : 0;
+    const int WB = Cfg::warp_bytes(R), AUX = Cfg::aux(R), RCW = Cfg::rcw(R);
     // everything below addresses shared memory through 32-bit shared-window addresses (LDS/STS, not generic LD/ST)
-    const uint32_t ring = smem_u32(base) + warp * Cfg::WARP_BYTES;
-    const uint32_t bcbuf = ring + LN_STAGES * Cfg::ITEM;
-    const uint32_t rcs = bcbuf + LN_BCS * Cfg::BC;
-    float* rc = reinterpret_cast<float*>(base + warp * Cfg::WARP_BYTES + LN_STAGES * Cfg::ITEM + LN_BCS * Cfg::BC);
-    const uint32_t full = smem_u32(base) + NW * Cfg::WARP_BYTES + warp * Cfg::NBARS * 8;
-    const uint32_t empty = full + LN_STAGES * 8;
-    const uint32_t bcfull = empty + LN_STAGES * 8;
+    const uint32_t ring = smem_u32(base) + warp * WB;
+    const uint32_t bcbuf = ring + Cfg::STAGES * Cfg::ITEM;
+    const uint32_t rcs = bcbuf + LN_BCS * AUX;
+    float* rc = reinterpret_cast<float*>(base + warp * WB + Cfg::STAGES * Cfg::ITEM + LN_BCS * AUX);
+    const uint32_t full = smem_u32(base) + NW * WB + warp * Cfg::NBARS * 8;
+    const uint32_t empty = full + Cfg::STAGES * 8;
+    const uint32_t bcfull = empty + Cfg::STAGES * 8;
     const uint32_t bcempty = bcfull + LN_BCS * 8;
 
-    // per-row constants {A[n]*s, bias*s', D, carry[n]}  (s = log2e, s' = 1 unless FAST: s = 1, s' = log2e)
+    // per-row constants {A[n]*s, bias*s', D, carry[n]}  (s = log2e, s' = 1 unless FAST: s = 1, s' = log2e), then the
+    // row's dt_proj weights (fused dt_proj): 16-bit weights packed two per word, zero-padded
     if (lane < w.nrows) {
-        float* k = rc + lane * RCF;
+        float* k = rc + lane * RCW;
 #pragma unroll
         for (int n = 0; n < NST; ++n) {
             k[n] = p.A[(w.d0 + lane) * NST + n] * (FAST ? 1.0f : kLog2e);
@@ -323,6 +410,17 @@ __device__ __forceinline__ void lanes_consumer(const ScanParams& p, uint8_t* bas
         }
         k[NST] = (p.bias ? p.bias[w.d0 + lane] : 0.0f) * (FAST ? kLog2e : 1.0f);
         k[NST + 1] = p.D ? p.D[w.d0 + lane] : 0.0f;
+        if constexpr (DTF) {
+            const IN_T* wr = (const IN_T*)p.wdt + (w.d0 + lane) * R;
+            uint32_t* kw = reinterpret_cast<uint32_t*>(k + RCF);
+            if constexpr (sizeof(IN_T) == 2) {
+                const unsigned short* ws = reinterpret_cast<const unsigned short*>(wr);
+                for (int q = 0; q < (R + 1) / 2; ++q)
+                    kw[q] = (uint32_t)ws[2 * q] | (2 * q + 1 < R ? (uint32_t)ws[2 * q + 1] << 16 : 0u);
+            } else {
+                for (int q = 0; q < R; ++q) kw[q] = __float_as_uint(to_f32(wr[q]));
+            }
+        }
     }
     __syncwarp();
 
@@ -339,10 +437,10 @@ __device__ __forceinline__ void lanes_consumer(const ScanParams& p, uint8_t* bas
         const int64_t tok0 = (int64_t)step * TOK + lane * C;       // first scan-order token of this lane
         const bool full_step = (int64_t)(step + 1) * TOK <= p.L;
         const int nv = full_step ? C : (int)max((int64_t)0, min((int64_t)C, p.L - tok0));
+        const int bs = step % LN_BCS;
         if (r == 0) {
-            const int bs = step % LN_BCS;
             mbar_wait_s(bcfull + bs * 8, (uint32_t)(step / LN_BCS) & 1u);
-            const uint32_t bc = bcbuf + bs * Cfg::BC + lane_off;
+            const uint32_t bc = bcbuf + bs * AUX + lane_off;
 #pragma unroll
             for (int n = 0; n < NST; ++n) {
                 lds_tokens<IN_T, C, REV>(bc + n * Cfg::CHUNK, Bv[n]);
@@ -353,25 +451,59 @@ __device__ __forceinline__ void lanes_consumer(const ScanParams& p, uint8_t* bas
                     if (!full_step && j >= nv) { Bv[n][j] = 0.0f; Cv[n][j] = 0.0f; }   // stale smem may hold NaN/Inf
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive_s(bcempty + bs * 8);
+            if constexpr (!DTF) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive_s(bcempty + bs * 8);
+            }
         }
         mbar_wait_s(full + slot * 8, phase);
         const uint32_t item = ring + slot * Cfg::ITEM + lane_off;
         float uv[C], dv[C], zv[HAS_Z ? C : 1];
         lds_tokens<IN_T, C, REV>(item, uv);
-        lds_tokens<IN_T, C, REV>(item + Cfg::CHUNK, dv);
-        if constexpr (HAS_Z) lds_tokens<IN_T, C, REV>(item + 2 * Cfg::CHUNK, zv);
+        if constexpr (!DTF) lds_tokens<IN_T, C, REV>(item + Cfg::CHUNK, dv);
+        if constexpr (HAS_Z) lds_tokens<IN_T, C, REV>(item + Cfg::ZOFF, zv);
         float kc[RCF];
 #pragma unroll
         for (int q = 0; q < RCF / 4; ++q) {
-            const uint4 t = lds128(rcs + (r * RCF + 4 * q) * 4);
+            const uint4 t = lds128(rcs + (r * RCW + 4 * q) * 4);
             kc[4 * q] = __uint_as_float(t.x); kc[4 * q + 1] = __uint_as_float(t.y);
             kc[4 * q + 2] = __uint_as_float(t.z); kc[4 * q + 3] = __uint_as_float(t.w);
         }
         __syncwarp();                                    // every lane has drained the slot (and read the row table)
         if (lane == 0) mbar_arrive_s(empty + slot * 8);  // hand it back to the producer
-        if (++slot == LN_STAGES) { slot = 0; phase ^= 1u; }
+        if (++slot == Cfg::STAGES) { slot = 0; phase ^= 1u; }
+
+        if constexpr (DTF) {
+            // fused dt_proj: delta[token] = sum_r w[row, r] * dts_r[r, token]; the rank rows sit in the step's aux buffer
+            const uint32_t xr = bcbuf + bs * AUX + 2 * NST * Cfg::CHUNK + lane_off;
+            const uint32_t wr = rcs + (r * RCW + RCF) * 4;
+#pragma unroll
+            for (int j = 0; j < C; ++j) dv[j] = 0.0f;
+            // XPoint's ranks (dt_rank = d_model / 16 = 6, 12) are fully unrolled so that the rank rows' LDS run ahead of
+            // the FMAs; other ranks take the rolled loop
+            auto rank_rows = [&](auto rr_tag) {
+                constexpr int RR = decltype(rr_tag)::value;      // 0 = runtime rank
+                const int Rn = RR ? RR : R;
+                if constexpr (sizeof(IN_T) == 2) {
+#pragma unroll(RR ? 16 : 1)
+                    for (int q = 0; q < Rn; q += 2) {
+                        const uint32_t w2 = lds32(wr + 2 * q);
+                        dt_accumulate<IN_T, C, REV>(xr + q * Cfg::CHUNK, w2 & 0xffffu, dv);
+                        if (q + 1 < Rn) dt_accumulate<IN_T, C, REV>(xr + (q + 1) * Cfg::CHUNK, w2 >> 16, dv);
+                    }
+                } else {
+#pragma unroll(RR ? 16 : 1)
+                    for (int q = 0; q < Rn; ++q) dt_accumulate<IN_T, C, REV>(xr + q * Cfg::CHUNK, lds32(wr + 4 * q), dv);
+                }
+            };
+            if (R == 6) rank_rows(std::integral_constant<int, 6>{});
+            else if (R == 12) rank_rows(std::integral_constant<int, 12>{});
+            else rank_rows(std::integral_constant<int, 0>{});
+            if (r == w.nrows - 1) {                      // last row of the step: the aux buffer is free again
+                __syncwarp();
+                if (lane == 0) mbar_arrive_s(bcempty + bs * 8);
+            }
+        }
 
         const float kb = kc[NST], kD = kc[NST + 1];
         auto body = [&](auto full_tag) {
@@ -415,7 +547,7 @@ __device__ __forceinline__ void lanes_consumer(const ScanParams& p, uint8_t* bas
                 const float hin = fmaf(Pe, hc, Se);
 #pragma unroll
                 for (int j = 0; j < C; ++j) y[j] = fmaf(fmaf(pl[j], hin, hl[j]), Cv[n][j], y[j]);
-                if (lane == 31) sts32(rcs + (r * RCF + NST + 2 + n) * 4, fmaf(P, hc, S_));
+                if (lane == 31) sts32(rcs + (r * RCW + NST + 2 + n) * 4, fmaf(P, hc, S_));
             }
             if constexpr (HAS_Z) {
 #pragma unroll
@@ -430,32 +562,33 @@ __device__ __forceinline__ void lanes_consumer(const ScanParams& p, uint8_t* bas
     __syncwarp();
     if (p.last && lane < w.nrows) {
 #pragma unroll
-        for (int n = 0; n < NST; ++n) p.last[(w.b * p.dim + w.d0 + lane) * NST + n] = rc[lane * RCF + NST + 2 + n];
+        for (int n = 0; n < NST; ++n) p.last[(w.b * p.dim + w.d0 + lane) * NST + n] = rc[lane * RCW + NST + 2 + n];
     }
 }
 
-template <int NST, typename IN_T, typename OUT_T, int C, bool HAS_Z, bool SOFTPLUS, int NW>
+template <int NST, typename IN_T, typename OUT_T, int C, bool HAS_Z, bool SOFTPLUS, int NW, bool DTF>
 __global__ void __launch_bounds__((NW + 1) * 32) scan_lanes_kernel(const ScanParams p) {
-    using Cfg = LanesCfg<NST, IN_T, C, HAS_Z, NW>;
+    using Cfg = LanesCfg<NST, IN_T, C, HAS_Z, NW, DTF>;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* base = smem_raw;
+    const int WB = Cfg::warp_bytes(DTF ? (int)p.R : 0);
     if (threadIdx.x == 0) {
-        uint64_t* bars = reinterpret_cast<uint64_t*>(base + NW * Cfg::WARP_BYTES);
+        uint64_t* bars = reinterpret_cast<uint64_t*>(base + NW * WB);
         for (int i = 0; i < NW * Cfg::NBARS; ++i) mbar_init(&bars[i], 1);
         fence_mbar_init();
         fence_proxy_async();
     }
     __syncthreads();
     if (warp == NW) {
-        lanes_producer<NST, IN_T, C, HAS_Z, NW>(p, base, lane);
+        lanes_producer<NST, IN_T, C, HAS_Z, NW, DTF>(p, base, lane);
         return;
     }
     const LanesWarp w = lanes_decode(p, (int64_t)blockIdx.x * NW + warp);
     if (!w.valid) return;
     const bool rev = w.g < 64 && ((p.rev_mask >> w.g) & 1);
-    if (rev) lanes_consumer<NST, IN_T, OUT_T, C, HAS_Z, SOFTPLUS, true, NW>(p, base, w, warp, lane);
-    else lanes_consumer<NST, IN_T, OUT_T, C, HAS_Z, SOFTPLUS, false, NW>(p, base, w, warp, lane);
+    if (rev) lanes_consumer<NST, IN_T, OUT_T, C, HAS_Z, SOFTPLUS, true, NW, DTF>(p, base, w, warp, lane);
+    else lanes_consumer<NST, IN_T, OUT_T, C, HAS_Z, SOFTPLUS, false, NW, DTF>(p, base, w, warp, lane);
 }
 
 // ============================================================================================
@@ -728,10 +861,10 @@ static int env_int(const char* name, int dflt) {
     return v && *v ? atoi(v) : dflt;
 }
 
-template <int NST, typename IN_T, typename OUT_T, int C, bool HAS_Z, bool SOFTPLUS, int NW>
+template <int NST, typename IN_T, typename OUT_T, int C, bool HAS_Z, bool SOFTPLUS, int NW, bool DTF>
 static int launch_lanes_cfg(const ScanParams& p, int64_t warps, cudaStream_t st) {
-    constexpr int smem = LanesCfg<NST, IN_T, C, HAS_Z, NW>::SMEM;
-    auto kern = scan_lanes_kernel<NST, IN_T, OUT_T, C, HAS_Z, SOFTPLUS, NW>;
+    const int smem = LanesCfg<NST, IN_T, C, HAS_Z, NW, DTF>::smem(DTF ? (int)p.R : 0);
+    auto kern = scan_lanes_kernel<NST, IN_T, OUT_T, C, HAS_Z, SOFTPLUS, NW, DTF>;
     XP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kern<<<(unsigned)ceil_div(warps, NW), (NW + 1) * 32, smem, st>>>(p);
     XP_LAUNCH_CHECK("scan_lanes_kernel");
@@ -740,13 +873,20 @@ static int launch_lanes_cfg(const ScanParams& p, int64_t warps, cudaStream_t st)
 
 template <int NST, typename IN_T, typename OUT_T, int C> static int launch_lanes_c(const ScanParams& p, int64_t warps, cudaStream_t st) {
     constexpr int NW = 4;
-    if (p.z) {
-        return p.softplus ? launch_lanes_cfg<NST, IN_T, OUT_T, C, true, true, NW>(p, warps, st)
-                          : launch_lanes_cfg<NST, IN_T, OUT_T, C, true, false, NW>(p, warps, st);
+    if (p.R > 0) {      // fused dt_proj (no z gate on this path: lanes_supports_dt)
+        return p.softplus ? launch_lanes_cfg<NST, IN_T, OUT_T, C, false, true, NW, true>(p, warps, st)
+                          : launch_lanes_cfg<NST, IN_T, OUT_T, C, false, false, NW, true>(p, warps, st);
     }
-    return p.softplus ? launch_lanes_cfg<NST, IN_T, OUT_T, C, false, true, NW>(p, warps, st)
-                      : launch_lanes_cfg<NST, IN_T, OUT_T, C, false, false, NW>(p, warps, st);
+    if (p.z) {
+        return p.softplus ? launch_lanes_cfg<NST, IN_T, OUT_T, C, true, true, NW, false>(p, warps, st)
+                          : launch_lanes_cfg<NST, IN_T, OUT_T, C, true, false, NW, false>(p, warps, st);
+    }
+    return p.softplus ? launch_lanes_cfg<NST, IN_T, OUT_T, C, false, true, NW, false>(p, warps, st)
+                      : launch_lanes_cfg<NST, IN_T, OUT_T, C, false, false, NW, false>(p, warps, st);
 }
+
+constexpr int LN_MAX_DT_RANK = 16;   // fused dt_proj on the lanes kernel (larger ranks: the aux buffers outgrow shared memory)
+static bool lanes_supports_dt(const ScanParams& p) { return p.R <= LN_MAX_DT_RANK && !p.z; }
 
 template <int NST, typename IN_T, typename OUT_T> static int launch_lanes(ScanParams p, cudaStream_t st) {
     const int64_t Dg = p.dim / p.groups;
@@ -761,7 +901,9 @@ template <int NST, typename IN_T, typename OUT_T> static int launch_lanes(ScanPa
     static const int c_override = env_int("XP_LANES_C", 0);   // tuning knob: 8 | 16
     if constexpr (NST == 1 && sizeof(IN_T) == 2) {
         const bool pads_more = ceil_div(p.L, 512) * 512 > ceil_div(p.L, 256) * 256;
-        if (c_override == 16 || (c_override != 8 && !pads_more)) return launch_lanes_c<NST, IN_T, OUT_T, 16>(p, warps, st);
+        // fused dt_proj: the R rank rows live in the aux buffers; keep at least two CTAs per SM
+        const bool too_big = p.R > 0 && LanesCfg<NST, IN_T, 16, false, 4, true>::smem((int)p.R) > 110 * 1024;
+        if (c_override == 16 || (c_override != 8 && !pads_more && !too_big)) return launch_lanes_c<NST, IN_T, OUT_T, 16>(p, warps, st);
     }
     return launch_lanes_c<NST, IN_T, OUT_T, 8>(p, warps, st);
 }
@@ -826,6 +968,12 @@ template <typename IN_T, typename OUT_T> static int dispatch(const ScanParams& p
     for (int64_t s : in_strides) vec_ok = vec_ok && (s % va == 0);
     vec_ok = vec_ok && (p.o_bs % vo == 0) && (p.o_ds % vo == 0);
     vec_ok = vec_ok && (p.u_gs % va == 0);
+    if (p.R > 0) {            // fused dt_proj: lanes kernel or the generic kernel
+        vec_ok = vec_ok && p.dl_gs % va == 0 && lanes_supports_dt(p);
+        if (vec_ok && p.dstate == 1) return launch_lanes<1, IN_T, OUT_T>(p, st);
+        if (vec_ok && p.dstate == 2) return launch_lanes<2, IN_T, OUT_T>(p, st);
+        return launch_generic<IN_T, OUT_T>(p, st);
+    }
     if (vec_ok && p.dstate == 1) return launch_lanes<1, IN_T, OUT_T>(p, st);
     if (vec_ok && p.dstate == 2) return launch_lanes<2, IN_T, OUT_T>(p, st);
     if (vec_ok && p.L % 8 == 0 && p.batch < 32768 * 65536LL) {   // whole 8-token steps; TMA coordinates are int32
@@ -868,6 +1016,13 @@ extern "C" int xp_selective_scan_fwd(const xp_scan_args* a, xp_stream_t stream) 
     if (a->u_group_div > 0) { p.u_gdiv = a->u_group_div; p.u_gs = a->u_group_stride; }
     else { p.u_gdiv = 1; p.u_gs = (a->dim / a->groups) * a->u_dim_stride; }
     p.rev_mask = a->reverse_group_mask;
+    p.wdt = nullptr; p.R = 0; p.dl_gs = 0;
+    if (a->dt_rank != 0) {
+        XP_REQUIRE(a->dt_rank > 0 && a->dt_rank <= 64, "fused dt_proj: dt_rank must be in 1..64 (got %lld)", (long long)a->dt_rank);
+        XP_REQUIRE(a->dt_weight != nullptr, "fused dt_proj: dt_weight is NULL");
+        XP_REQUIRE(a->delta_dim == a->dim, "fused dt_proj needs delta_dim == dim");
+        p.wdt = a->dt_weight; p.R = a->dt_rank; p.dl_gs = a->dt_group_stride;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     const int key = a->in_dtype * 4 + a->out_dtype;
     switch (key) {

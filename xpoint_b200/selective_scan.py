@@ -23,7 +23,7 @@ import torch
 from . import _lib
 
 
-def _check_shapes(u, delta, A, B, C, D, z, delta_bias, u_group_div=1):
+def _check_shapes(u, delta, A, B, C, D, z, delta_bias, u_group_div=1, dt_weight=None):
     if u.dim() != 3:
         raise RuntimeError("u must have shape (batch, dim, seqlen)")
     batch, dim, L = u.shape
@@ -36,9 +36,18 @@ def _check_shapes(u, delta, A, B, C, D, z, delta_bias, u_group_div=1):
     if B.dim() != 4 or C.dim() != 4:
         raise RuntimeError("B and C must have shape (batch, groups, dstate, seqlen) or (batch, dstate, seqlen)")
     groups, N = B.shape[1], B.shape[2]
-    if delta.dim() != 3 or delta.shape[0] != batch or delta.shape[2] != L:
-        raise RuntimeError(f"delta must have shape (batch, delta_dim, seqlen), got {tuple(delta.shape)}")
-    ddim = delta.shape[1]
+    if dt_weight is not None:     # fused dt_proj: delta holds the low-rank factors dts_r (batch, groups, dt_rank, seqlen)
+        if delta.dim() != 4 or delta.shape[0] != batch or delta.shape[1] != groups or delta.shape[3] != L:
+            raise RuntimeError(f"with dt_weight, delta must be dts_r (batch, groups, dt_rank, seqlen), got {tuple(delta.shape)}")
+        if tuple(dt_weight.shape) != (dim, delta.shape[2]) or dt_weight.dtype != u.dtype:
+            raise RuntimeError(f"dt_weight must have shape (dim, dt_rank) = ({dim}, {delta.shape[2]}) and u's dtype")
+        if not 1 <= delta.shape[2] <= 64:
+            raise RuntimeError("fused dt_proj supports dt_rank 1..64")
+        ddim = dim
+    else:
+        if delta.dim() != 3 or delta.shape[0] != batch or delta.shape[2] != L:
+            raise RuntimeError(f"delta must have shape (batch, delta_dim, seqlen), got {tuple(delta.shape)}")
+        ddim = delta.shape[1]
     if tuple(A.shape) != (dim, N):
         raise RuntimeError(f"A must have shape (dim, dstate) = ({dim}, {N}), got {tuple(A.shape)}")
     if tuple(B.shape) != (batch, groups, N, L) or tuple(C.shape) != (batch, groups, N, L):
@@ -72,14 +81,17 @@ def _last_contig(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 
 
 def scan_forward(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False, out_float=True,
-                 return_last_state=False, force_generic=False, u_group_div=1, reverse_group_mask=0):
+                 return_last_state=False, force_generic=False, u_group_div=1, reverse_group_mask=0, dt_weight=None):
     """One call of xp_selective_scan_fwd.  Returns (out, last_state or None).
 
     ``u_group_div`` / ``reverse_group_mask`` expose the fused-CrossScan addressing of the C ABI (xp_scan_args):
     with ``u_group_div = q > 1`` u has shape (batch, dim / q, seqlen) and groups g, g+1, .. g+q-1 (g % q == 0) all read
-    source g / q; bit g of the mask makes group g run backwards through memory (its output stays unflipped)."""
+    source g / q; bit g of the mask makes group g run backwards through memory (its output stays unflipped).
+
+    ``dt_weight`` (dim, dt_rank) selects the fused dt_proj of the C ABI: ``delta`` is then the low-rank
+    dts_r (batch, groups, dt_rank, seqlen) of VMamba.py:605-615 and delta = dt_weight x dts_r is formed inside the scan."""
     dev = _lib.require_cuda(u, delta, A, B, C, D, z, delta_bias)
-    B, C, batch, dim, ddim, groups, N, L = _check_shapes(u, delta, A, B, C, D, z, delta_bias, u_group_div)
+    B, C, batch, dim, ddim, groups, N, L = _check_shapes(u, delta, A, B, C, D, z, delta_bias, u_group_div, dt_weight)
     u, delta, B, C, z = map(_last_contig, (u, delta, B, C, z))
     A = A.contiguous()
     D = None if D is None else D.contiguous()
@@ -100,7 +112,12 @@ def scan_forward(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softp
     a.last_state = 0 if last is None else last.data_ptr()
     a.batch, a.dim, a.delta_dim, a.groups, a.dstate, a.seqlen = batch, dim, ddim, groups, N, L
     a.u_batch_stride, a.u_dim_stride = u.stride(0), u.stride(1)
-    a.delta_batch_stride, a.delta_dim_stride = delta.stride(0), delta.stride(1)
+    if dt_weight is None:
+        a.delta_batch_stride, a.delta_dim_stride = delta.stride(0), delta.stride(1)
+    else:
+        dt_weight = dt_weight.contiguous()
+        a.delta_batch_stride, a.dt_group_stride, a.delta_dim_stride = delta.stride(0), delta.stride(1), delta.stride(2)
+        a.dt_weight, a.dt_rank = dt_weight.data_ptr(), delta.shape[2]
     a.B_batch_stride, a.B_group_stride, a.B_state_stride = B.stride(0), B.stride(1), B.stride(2)
     a.C_batch_stride, a.C_group_stride, a.C_state_stride = C.stride(0), C.stride(1), C.stride(2)
     if z is not None:
@@ -121,16 +138,20 @@ def scan_forward(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softp
         _lib.check(_lib.lib().xp_selective_scan_fwd(ctypes.byref(a), _lib.stream_ptr(dev)))
         if prof is not None:
             e1.record()
-            prof.append((e0, e1, algorithmic_bytes(batch, dim, groups, N, L, u.element_size(), out.element_size()),
-                         (batch, dim, groups, N, L, str(u.dtype), str(out.dtype))))
+            rank = 0 if dt_weight is None else delta.shape[2]
+            prof.append((e0, e1, algorithmic_bytes(batch, dim, groups, N, L, u.element_size(), out.element_size(), rank),
+                         (batch, dim, groups, N, L, str(u.dtype), str(out.dtype), rank)))
     _lib.count_launches(1)
     return out, last
 
 
-def algorithmic_bytes(batch, dim, groups, dstate, L, s_in, s_out):
+def algorithmic_bytes(batch, dim, groups, dstate, L, s_in, s_out, dt_rank=0):
     """Op-level bytes the selective_scan_fn contract reads and writes once:
-    B*L*[(2*KD + 2*K*N)*s_in + KD*s_out] + 4*KD*(N+2)."""
-    return batch * L * ((2 * dim + 2 * groups * dstate) * s_in + dim * s_out) + 4 * dim * (dstate + 2)
+    B*L*[(2*KD + 2*K*N)*s_in + KD*s_out] + 4*KD*(N+2).
+    With the fused dt_proj the delta term KD*s_in becomes K*R*s_in (plus the (KD, R) weights once)."""
+    delta_term = groups * dt_rank if dt_rank else dim
+    return (batch * L * ((dim + delta_term + 2 * groups * dstate) * s_in + dim * s_out) + 4 * dim * (dstate + 2)
+            + dim * dt_rank * s_in)
 
 
 class _OflexModule:

@@ -228,6 +228,7 @@ class SS2D(nn.Module):
                 wx=wx.expand(batch, -1, -1, -1).contiguous(),                     # (B, 2, 2(R+2N), D)
                 wdt=wdt.expand(batch, -1, -1, -1, -1).contiguous(),               # (B, 2, 2, D, R)
                 wdt32=self.dt_projs_weight.detach().float()[order].contiguous(),  # (4, D, R) for xp_ss2d_dt_proj
+                wdt_scan=self.dt_projs_weight.detach()[order].reshape(K * D, R).to(dtype).contiguous(),   # fused dt_proj
                 A=(-self.A_logs.detach().float().exp()).view(K, D, N)[order].reshape(K * D, N).contiguous(),
                 Ds=self.Ds.detach().float().view(K, D)[order].reshape(-1).contiguous(),
                 dt_bias=self.dt_projs_bias.detach().float()[order].reshape(-1).contiguous(),
@@ -249,6 +250,13 @@ class SS2D(nn.Module):
         w = self._fused_weights(B, xx.dtype)
         x_dbl = torch.matmul(w["wx"], xx)                                          # (B, 2, 2(R+2N), L)
         x_dbl = x_dbl.view(B, K, R + 2 * N, L)
+        if N <= 2 and R <= 16 and L % 8 == 0 and not getattr(self, "disable_dt_fusion", False):
+            # the scan forms delta = W_dt x dts_r itself, the (B, K*D, L) delta never reaches HBM
+            ys, _ = scan_forward(xx.view(B, 2 * D, L), x_dbl[:, :, :R], w["A"], x_dbl[:, :, R:R + N], x_dbl[:, :, R + N:],
+                                 w["Ds"], None, w["dt_bias"], True, True, u_group_div=2,
+                                 reverse_group_mask=_ss2d.REVERSE_MASK, dt_weight=w["wdt_scan"])
+            return _ss2d.ss2d_merge_norm(ys.view(B, K, D, L), H, W, w["norm_w"], w["norm_b"], zact, self.out_norm.eps,
+                                         out_dtype=out_dtype or xx.dtype)
         if _ss2d.dt_proj_supported(R, L, x_dbl.dtype, B * K):
             dts = _ss2d.ss2d_dt_proj(x_dbl[:, :, :R], w["wdt32"])                  # (B, 4, D, L), store-bound kernel
         else:

@@ -77,8 +77,10 @@ XP_API int xp_check_device(void);
  * and the (batch, dim, seqlen) delta never exists in HBM: `delta` points at dts_r (batch, groups, dt_rank, seqlen) in
  * in_dtype with element strides delta_batch_stride / dt_group_stride / delta_dim_stride (= rank-row stride), dt_weight is
  * (dim, dt_rank) contiguous in in_dtype, and
- *     delta_l[d] = sum_r dt_weight[d, r] * dts_r[b, g(d), r, l]        (exact products, fp32 accumulation, r ascending)
- * before delta_bias / softplus.  delta_dim must equal dim.  dt_rank <= 64.
+ *     delta_l[d] = round_to_in_dtype( sum_r dt_weight[d, r] * dts_r[b, g(d), r, l] )      (fp32 accumulation)
+ * before delta_bias / softplus -- the value the reference's dt_proj GEMM produces under autocast.  delta_dim must equal
+ * dim.  dt_rank <= 64; 16-bit inputs with dt_rank <= 16 and dstate <= 2 run the rank-R product on the tensor cores inside
+ * the scan kernel (mma.sync, one MMA along the rank), everything else takes the shape-generic kernel.
  */
 typedef struct {
     const void* u;
@@ -224,6 +226,24 @@ XP_API int xp_detector_post(const void* logits, float* prob, int64_t B, int64_t 
  */
 XP_API int xp_l2_normalize(const void* x, float* out_cf, float* out_cl, int64_t B, int64_t C, int64_t HW, int32_t dtype,
                     xp_stream_t stream);
+
+/* Channel-last forms (the drop-in model runs the heads' 1x1 convolutions as GEMMs on (cells, C) rows; these read the GEMM
+ * outputs where they lie):
+ *   xp_detector_post_cl: logits (B*Hc*Wc, ld) rows, the first r*r+1 entries of a row are the cell's logits (ld >= r*r+1,
+ *                        e.g. 72 for a 16-byte aligned 65-wide GEMM) -> prob (B, 1, r*Hc, r*Wc) fp32.
+ *   xp_l2_normalize_cl:  x (B, HW, C) rows -> out_cf (B, C, HW) and/or out_cl (B, HW, C) fp32, unit L2 norm per row.
+ *   xp_encoder_tail:     the VSSM output path feeding the heads, one pass: s = x [+ pend] on the last stage's channel-last
+ *                        (B, H, W, C_out*bs*bs) residual stream (x fp32, pend any dtype or NULL) -> depth_to_space(bs)
+ *                        (VMamba.py:1500-1505) -> enc_out (B, C_out, H*bs, W*bs) fp32 channel-first (the model's
+ *                        `encoder_output`, XPoint.py:309; nullable) and `padded` (B, H*bs+2, W*bs+2, C_out) channel-last in
+ *                        pad_dtype = ReflectionPad2d(1) of it (XPoint.py:112,125; nullable).  C_out in {8, 16, 32, 48, 64}. */
+XP_API int xp_detector_post_cl(const void* logits, float* prob, int64_t B, int64_t Hc, int64_t Wc, int32_t r, int64_t ld,
+                               int32_t dtype, xp_stream_t stream);
+XP_API int xp_l2_normalize_cl(const void* x, float* out_cf, float* out_cl, int64_t B, int64_t C, int64_t HW, int32_t dtype,
+                              xp_stream_t stream);
+XP_API int xp_encoder_tail(const void* x, const void* pend, float* enc_out, void* padded, int64_t B, int64_t H, int64_t W,
+                           int64_t C_out, int64_t bs, int32_t x_dtype, int32_t pend_dtype, int32_t pad_dtype,
+                           xp_stream_t stream);
 
 /* -- a8/a9: greedy box NMS + top-k + keypoint compaction ------------------------------
  * Replaces utils.box_nms (xpoint/utils/utils.py:148-192, i.e. torchvision.ops.nms/batched_nms on

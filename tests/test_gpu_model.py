@@ -80,8 +80,9 @@ def test_ss2d_fused_dt_proj_matches_materialised_delta(dtype, C):
     m = X.SS2D(d_model=C, d_state=1, ssm_ratio=1.0, forward_type="v05_noz", conv_bias=False).to(DEV).eval()
     x = torch.randn(2, 32, 40, C, device=DEV)
     with torch.no_grad(), torch.autocast("cuda", dtype=dtype, enabled=dtype != torch.float32):
+        m.fuse_dt_proj = True
         y = m(x)
-        m.disable_dt_fusion = True
+        m.fuse_dt_proj = False
         ym = m(x)
     assert_close(y.float().cpu().numpy(), ym.float().cpu().numpy(), 2e-5 if dtype == torch.float32 else 1e-2, f"C={C} {dtype}")
 

@@ -170,7 +170,7 @@ def test_fused_cross_scan_addressing(dtype, N, L, use_z):
 def test_fused_dt_proj(dtype, N, R, L, addressing):
     """xp_scan_args.dt_weight / dt_rank (ABI 3): the scan forms delta = dt_projs_weight x dts_r itself
     (VMamba.py:605-615) from a strided view of the x_proj output.  The oracle gets the materialised fp32 delta.  Ranks
-    <= 16 with N <= 2 run on the lanes kernel (FHFMA for 16-bit inputs), everything else on the generic kernel; "ss2d"
+    <= 16 with N <= 2 and 16-bit inputs run on the lanes kernel (mma.sync micro-GEMM), everything else on the generic kernel; "ss2d"
     adds the shared-u / reversed-group addressing of the copy-free SS2D path."""
     X, O = _imports()
     from xpoint_b200.selective_scan import scan_forward
@@ -181,7 +181,7 @@ def test_fused_dt_proj(dtype, N, R, L, addressing):
     x_dbl[:, :, :R] *= 0.3
     wdt = (torch.randn(K * Dg, R, generator=g) * R ** -0.5).to(dtype)
     dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
-    delta = torch.from_numpy(O.dt_proj(dts, wdt))
+    delta = torch.from_numpy(O.dt_proj(dts, wdt)).to(dtype).float()     # rounded like the reference's dt_proj output
     div, mask = (2, 0b1010) if addressing == "ss2d" else (1, 0)
     rev = [bool((mask >> k) & 1) for k in range(K)]
     usrc = u[:, : (K // div) * Dg].contiguous()
@@ -203,9 +203,10 @@ def test_fused_dt_proj(dtype, N, R, L, addressing):
     for force_generic in (False, True):
         out, last = scan_forward(usrc.to(DEV), dts_d, A.to(DEV), Bs_d, Cs_d, D.to(DEV), None, bias.to(DEV), True, True, True,
                                  force_generic=force_generic, u_group_div=div, reverse_group_mask=mask, dt_weight=wdt.to(DEV))
-        # identical pre-rounded factors on both sides and fp32 accumulation: the fp32 bar holds for 16-bit inputs too
-        assert_close(out.cpu().numpy(), ref, FP32_REL, f"fused dt_proj {dtype} N={N} R={R} L={L} generic={force_generic}")
-        assert_close(last.cpu().numpy(), rlast, FP32_REL, "fused dt_proj last state")
+        # identical pre-rounded factors on both sides; a different fp32 summation order can move a 16-bit delta by one ulp
+        tol = FP32_REL if dtype == torch.float32 else 2e-3
+        assert_close(out.cpu().numpy(), ref, tol, f"fused dt_proj {dtype} N={N} R={R} L={L} generic={force_generic}")
+        assert_close(last.cpu().numpy(), rlast, tol, "fused dt_proj last state")
 
 
 def test_fused_dt_proj_errors():

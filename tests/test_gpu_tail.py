@@ -30,6 +30,56 @@ def test_heads_golden():
     np.testing.assert_allclose(p16.cpu().numpy(), ref16.numpy(), rtol=1e-5, atol=1e-7)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("ld", [65, 72, 80])
+def test_channel_last_head_kernels(dtype, ld):
+    """xp_detector_post_cl / xp_l2_normalize_cl consume the heads' GEMM outputs as (cells, C) rows: same results as the
+    channel-first kernels (which are pinned to the reference goldens above) on the permuted tensors."""
+    import xpoint_b200.postprocess as P
+    g = torch.Generator().manual_seed(ld)
+    B, Hc, Wc = 3, 9, 13
+    rows = torch.randn(B * Hc * Wc, ld, generator=g).to(dtype).to(DEV)
+    cf = rows[:, :65].reshape(B, Hc, Wc, 65).permute(0, 3, 1, 2).contiguous()
+    assert torch.equal(P.detector_post_rows(rows, B, Hc, Wc, 8), P.detector_post(cf, 8))
+    assert torch.equal(P.detector_post_rows(rows[:, 1:], B, Hc, Wc, 8) if ld > 65 else P.detector_post_rows(rows, B, Hc, Wc, 8),
+                       P.detector_post(rows[:, 1:66].reshape(B, Hc, Wc, 65).permute(0, 3, 1, 2).contiguous(), 8)
+                       if ld > 65 else P.detector_post(cf, 8))                          # unaligned rows take the scalar loads
+    d = torch.randn(B * Hc * Wc, 256, generator=g).to(dtype).to(DEV)
+    dcf = d.reshape(B, Hc, Wc, 256).permute(0, 3, 1, 2).contiguous()
+    ref, ref_cl = P.normalize_descriptors(dcf, channel_last_copy=True)
+    out, out_cl = P.normalize_descriptor_rows(d, B, Hc, Wc)
+    assert torch.allclose(out, ref, rtol=1e-6, atol=1e-7) and torch.allclose(out_cl, ref_cl, rtol=1e-6, atol=1e-7)
+    assert torch.equal(out_cl, out.permute(0, 2, 3, 1).contiguous())
+    none, only_cl = P.normalize_descriptor_rows(d, B, Hc, Wc, want_channel_first=False)
+    assert none is None and torch.equal(only_cl, out_cl)
+
+
+@pytest.mark.parametrize("CO,pdt,odt", [(48, torch.float16, torch.float16), (8, torch.float32, torch.float32),
+                                        (64, torch.bfloat16, torch.bfloat16), (16, None, torch.float16), (32, torch.float16, None)])
+def test_encoder_tail_vs_torch(CO, pdt, odt):
+    """x + branch -> permute -> depth_to_space(4) (VMamba.py:1500-1505,1521-1523) -> clone -> ReflectionPad2d(1) ->
+    compute dtype, channels-last: exact."""
+    import xpoint_b200 as X
+    import xpoint_b200.postprocess as P
+    g = torch.Generator().manual_seed(CO)
+    B, H, W = 3, 5, 7
+    x = torch.randn(B, H, W, CO * 16, generator=g).to(DEV)
+    pend = None if pdt is None else torch.randn(B, H, W, CO * 16, generator=g).to(pdt).to(DEV)
+    assert P.encoder_tail_supported(x)
+    enc, padded = P.encoder_tail(x, pend, 4, pad_dtype=odt)
+    s = x if pend is None else x + pend
+    ref = X.VSSM.depth_to_space(s.permute(0, 3, 1, 2), 4)
+    assert torch.equal(enc, ref)
+    if odt is None:
+        assert padded is None
+    else:
+        refp = torch.nn.ReflectionPad2d(1)(ref).to(odt)
+        assert padded.shape == refp.shape and padded.is_contiguous(memory_format=torch.channels_last)
+        assert torch.equal(padded, refp)
+    enc2, _ = P.encoder_tail(x, pend, 4, pad_dtype=odt, want_encoder_output=False) if odt is not None else (None, None)
+    assert enc2 is None
+
+
 def test_nms_golden_bit_exact():
     X, _ = _imports()
     g = golden("tail")

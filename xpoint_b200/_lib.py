@@ -57,6 +57,9 @@ _SIGNATURES = {
     "xp_linear_act": (ctypes.c_int, [c_void_p] * 4 + [c_int64] * 3 + [c_int32, c_int32, c_void_p]),
     "xp_detector_post": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32, c_void_p]),
     "xp_l2_normalize": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_void_p]),
+    "xp_detector_post_cl": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int64, c_int32, c_void_p]),
+    "xp_l2_normalize_cl": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_void_p]),
+    "xp_encoder_tail": (ctypes.c_int, [c_void_p] * 4 + [c_int64] * 5 + [c_int32] * 3 + [c_void_p]),
     "xp_nms_workspace_bytes": (c_int64, [c_int64] * 3),
     "xp_box_nms": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float, c_float, c_float, c_int64,
                                   c_float, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),

@@ -46,26 +46,13 @@ __device__ __forceinline__ float delta_act(float d, float bias, int softplus) {
     return softplus ? softplus_f(d) : d;
 }
 
-// acc + a*b with 16-bit a, b and an fp32 accumulator in ONE instruction (FHFMA, sm_100 mixed-precision fma): the product
-// of two 16-bit floats is exact in fp32, so this equals fmaf(float(a), float(b), acc).
-template <typename IN_T> __device__ __forceinline__ float fma_mixed(unsigned short a, unsigned short b, float acc);
-template <> __device__ __forceinline__ float fma_mixed<__half>(unsigned short a, unsigned short b, float acc) {
-    float d;
-    asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"(a), "h"(b), "f"(acc));
-    return d;
-}
-template <> __device__ __forceinline__ float fma_mixed<__nv_bfloat16>(unsigned short a, unsigned short b, float acc) {
-    float d;
-    asm("fma.rn.f32.bf16 %0, %1, %2, %3;" : "=f"(d) : "h"(a), "h"(b), "f"(acc));
-    return d;
-}
-
-// delta of one token from the low-rank factors (fused dt_proj): sum_r w[r] * x[r*xs + l], r ascending, fp32 accumulation
+// delta of one token from the low-rank factors (fused dt_proj): sum_r w[r] * x[r*xs + l], fp32 accumulation, rounded to
+// the input dtype like the output of the reference's dt_proj GEMM (VMamba.py:607-608 under autocast)
 template <typename IN_T>
 __device__ __forceinline__ float delta_lowrank(const IN_T* x, int64_t xs, const IN_T* w, int R, int64_t l) {
     float acc = 0.0f;
     for (int r = 0; r < R; ++r) acc = fmaf(to_f32(w[r]), to_f32(x[r * xs + l]), acc);
-    return acc;
+    return to_f32(from_f32<IN_T>(acc));
 }
 
 // ============================================================================================
@@ -231,24 +218,29 @@ __device__ __forceinline__ void store_tokens(OUT_T* gp, const float (&y)[C], int
     }
 }
 
+// Fused dt_proj (DTF, 16-bit inputs only): delta = W_dt x dts_r is a rank-R micro-GEMM.  Per step a consumer warp
+// multiplies its 8 rows' weights (A operand, constant registers) with the step's dts_r rows (B operand, ldmatrix.trans
+// straight from the TMA-filled tile) on the tensor cores (mma.sync m16n8k8 / m16n8k16, fp32 accumulate -- rows 8..15 of
+// the M=16 tile are zero padding), rounds the result to the input dtype exactly where the reference's dt_proj GEMM does
+// (F.conv1d / einsum under autocast, VMamba.py:607-608) and parks it in a per-warp [8 rows][TOK] tile that the row loop
+// reads like a materialised delta chunk.  Row stride = CHUNK + 16 bytes: conflict-free for ldmatrix, the packed
+// stores and the row loop's LDS.128.
 template <int NST, typename IN_T, int C, bool HAS_Z, int NW, bool DTF> struct LanesCfg {
     static constexpr int TOK = 32 * C;                                   // tokens per step
     static constexpr int CHUNK = TOK * (int)sizeof(IN_T);                // bytes of one row chunk
     static constexpr int ITEM = CHUNK * ((HAS_Z ? 2 : 1) + (DTF ? 0 : 1));   // u [, delta] [, z]
     static constexpr int ZOFF = CHUNK * (DTF ? 1 : 2);
-    static constexpr int RCF = NST == 1 ? 4 : 8;                         // floats of per-row scalar constants
-    // fused dt_proj with 512-token steps: the R rank rows dominate shared memory; a 2-deep u ring keeps 3 CTAs per SM
-    static constexpr int STAGES = (DTF && C == 16) ? 2 : LN_STAGES;
-    static constexpr int NBARS = 2 * STAGES + 2 * LN_BCS;                // full/empty + bcfull/bcempty
-    // The rest depends on the dt rank R of the fused dt_proj (R = 0 unless DTF: everything folds to constants).
-    //   aux buffer: B rows, C rows, then the R rows of dts_r; row table: RCF scalars + the row's dt weights
-    __host__ __device__ static constexpr int aux(int R) { return (2 * NST + (DTF ? R : 0)) * CHUNK; }
-    __host__ __device__ static constexpr int wwords(int R) {
-        return DTF ? ((((int)sizeof(IN_T) == 2 ? (R + 1) / 2 : R) + 3) & ~3) : 0;
-    }
-    __host__ __device__ static constexpr int rcw(int R) { return RCF + wwords(R); }
+    static constexpr int BC = 2 * NST * CHUNK;                           // B rows then C rows
+    static constexpr int RCF = NST == 1 ? 4 : 8;                         // floats of per-row constants
+    static constexpr int RC_BYTES = LN_MAXROWS * RCF * 4;
+    static constexpr int DROW = CHUNK + 16;                              // padded row stride of the dts_r / delta tiles
+    static constexpr int DTILE = LN_MAXROWS * DROW;                      // delta tile: one row per channel row of the warp
+    static constexpr int NBARS = 2 * LN_STAGES + 2 * LN_BCS + (DTF ? 2 : 0);   // full/empty, bcfull/bcempty [, dfull/dempty]
+    // dts_r tile: the rank padded to the MMA's K (8 or 16); R = 0 unless DTF, everything folds to constants then
+    __host__ __device__ static constexpr int rpad(int R) { return R <= 8 ? 8 : 16; }
+    __host__ __device__ static constexpr int dts_bytes(int R) { return DTF ? rpad(R) * DROW : 0; }
     __host__ __device__ static constexpr int warp_bytes(int R) {
-        return STAGES * ITEM + LN_BCS * aux(R) + LN_MAXROWS * rcw(R) * 4;
+        return LN_STAGES * ITEM + LN_BCS * BC + dts_bytes(R) + (DTF ? DTILE : 0) + RC_BYTES;
     }
     __host__ __device__ static constexpr int smem(int R) { return NW * (warp_bytes(R) + NBARS * 8) + 16; }
 };
@@ -278,15 +270,18 @@ __device__ __forceinline__ void lanes_producer(const ScanParams& p, uint8_t* bas
     constexpr int TOK = Cfg::TOK;
     constexpr int ES = (int)sizeof(IN_T);
     const int R = DTF ? (int)p.R : 0;
-    const int WB = Cfg::warp_bytes(R), AUX = Cfg::aux(R);
+    const int WB = Cfg::warp_bytes(R);
     const bool mine = lane < NW;
     const LanesWarp w = lanes_decode(p, (int64_t)blockIdx.x * NW + (mine ? lane : 0));
     uint8_t* ring = base + (mine ? lane : 0) * WB;
-    uint8_t* bcbuf = ring + Cfg::STAGES * Cfg::ITEM;
+    uint8_t* bcbuf = ring + LN_STAGES * Cfg::ITEM;
+    uint8_t* dts = bcbuf + LN_BCS * Cfg::BC;
     uint64_t* full = reinterpret_cast<uint64_t*>(base + NW * WB) + (mine ? lane : 0) * Cfg::NBARS;
-    uint64_t* empty = full + Cfg::STAGES;
-    uint64_t* bcfull = empty + Cfg::STAGES;
+    uint64_t* empty = full + LN_STAGES;
+    uint64_t* bcfull = empty + LN_STAGES;
     uint64_t* bcempty = bcfull + LN_BCS;
+    uint64_t* dfull = bcempty + LN_BCS;      // DTF only
+    uint64_t* dempty = dfull + 1;
     const int64_t Dg = p.dim / p.groups;
     const int64_t dg0 = w.d0 - w.g * Dg;
     const bool rev = (p.rev_mask >> (w.g & 63)) & 1 && w.g < 64;
@@ -308,6 +303,7 @@ __device__ __forceinline__ void lanes_producer(const ScanParams& p, uint8_t* bas
             bool ok = mbar_test_wait(&empty[slot], (fill - 1u) & 1u);          // fill 0: parity 1 passes on a fresh barrier
             const int bs = step % LN_BCS;
             if (ok && r == 0) ok = mbar_test_wait(&bcempty[bs], ((uint32_t)(step / LN_BCS) - 1u) & 1u);
+            if (DTF && ok && r == 0) ok = mbar_test_wait(dempty, ((uint32_t)step - 1u) & 1u);
             if (ok) {
                 const int64_t t0 = (int64_t)step * TOK;
                 const int64_t valid = min((int64_t)TOK, p.L - t0);
@@ -320,21 +316,21 @@ __device__ __forceinline__ void lanes_producer(const ScanParams& p, uint8_t* bas
                 if (!DTF) bulk_load(dst + Cfg::CHUNK, db + r * p.dl_ds + m0, bytes, &full[slot]);
                 if (HAS_Z) bulk_load(dst + Cfg::ZOFF, zb + r * p.z_ds + m0, bytes, &full[slot]);
                 if (r == 0) {
-                    uint8_t* bc = bcbuf + bs * AUX + off;
-                    mbar_arrive_expect_tx(&bcfull[bs], bytes * (2 * NST + R));
+                    uint8_t* bc = bcbuf + bs * Cfg::BC + off;
+                    mbar_arrive_expect_tx(&bcfull[bs], bytes * 2 * NST);
 #pragma unroll
                     for (int n = 0; n < NST; ++n) {
                         bulk_load(bc + n * Cfg::CHUNK, Bb + n * p.B_ss + m0, bytes, &bcfull[bs]);
                         bulk_load(bc + (NST + n) * Cfg::CHUNK, Cb + n * p.C_ss + m0, bytes, &bcfull[bs]);
                     }
-                    if (DTF) {
+                    if (DTF) {                                                  // the step's dts_r rows (single buffer)
+                        mbar_arrive_expect_tx(dfull, bytes * R);
 #pragma unroll 1
-                        for (int q = 0; q < R; ++q)
-                            bulk_load(bc + (2 * NST + q) * Cfg::CHUNK, db + q * p.dl_ds + m0, bytes, &bcfull[bs]);
+                        for (int q = 0; q < R; ++q) bulk_load(dts + q * Cfg::DROW + off, db + q * p.dl_ds + m0, bytes, dfull);
                     }
                 }
                 if (++r == w.nrows) { r = 0; ++step; }
-                if (++slot == Cfg::STAGES) { slot = 0; ++fill; }
+                if (++slot == LN_STAGES) { slot = 0; ++fill; }
                 ++it;
                 issued = true;
             }
@@ -343,43 +339,80 @@ __device__ __forceinline__ void lanes_producer(const ScanParams& p, uint8_t* bas
     }
 }
 
-// dv[j] += w * x[j] for the C tokens of this lane, x read from shared memory (one dts_r rank row), REV mirrors the order.
-// 16-bit: the raw packed halves feed FHFMA directly (no widening); `w` holds the weight in the low 16 bits.
-template <typename IN_T, int C, bool REV>
-__device__ __forceinline__ void dt_accumulate(uint32_t saddr, uint32_t w, float (&dv)[C]) {
-    if constexpr (sizeof(IN_T) == 2) {
+// ---- tensor-core pieces of the fused dt_proj ----
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t saddr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+// D(16x8, fp32) = A(16xK) * B(Kx8); only rows 0..7 of A are populated (a1 / a3 = rows 8..15 = 0), so d[2], d[3] stay 0
+template <typename IN_T> __device__ __forceinline__ void mma_k8(float (&d)[4], uint32_t a0, uint32_t b0);
+template <> __device__ __forceinline__ void mma_k8<__half>(float (&d)[4], uint32_t a0, uint32_t b0) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%7,%7,%7,%7};"
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]) : "r"(a0), "r"(0u), "r"(b0), "f"(0.0f));
+}
+template <> __device__ __forceinline__ void mma_k8<__nv_bfloat16>(float (&d)[4], uint32_t a0, uint32_t b0) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%7,%7,%7,%7};"
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]) : "r"(a0), "r"(0u), "r"(b0), "f"(0.0f));
+}
+template <typename IN_T> __device__ __forceinline__ void mma_k16(float (&d)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1);
+template <> __device__ __forceinline__ void mma_k16<__half>(float (&d)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]) : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1), "f"(0.0f));
+}
+template <> __device__ __forceinline__ void mma_k16<__nv_bfloat16>(float (&d)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]) : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1), "f"(0.0f));
+}
+template <typename IN_T> __device__ __forceinline__ uint32_t pack2(float lo, float hi);
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float lo, float hi) {
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float lo, float hi) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2<float>(float, float) { return 0u; }   // never used (DTF is 16-bit only)
+__device__ __forceinline__ void sts_u32(uint32_t saddr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" :: "r"(saddr), "r"(v) : "memory");
+}
+
+// delta tile [8 rows][TOK] (row stride DROW) = W (A fragments a_lo, a_hi: this lane's row lane/4, ranks 2*(lane%4)+{0,1}
+// and +8) x dts_r tile [rpad rows][TOK]
+template <typename IN_T, int TOK, int DROW>
+__device__ __forceinline__ void dt_tile_mma(uint32_t dts, uint32_t dtile, uint32_t a_lo, uint32_t a_hi, bool k16, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    const uint32_t out = dtile + g * DROW + t * 4;           // tokens 2t, 2t+1 of row g
+    const int mi = lane >> 3, kr = lane & 7;                 // ldmatrix: lane supplies row kr of matrix mi
+    if (!k16) {
+        // four 8x8 matrices = ranks 0..7 x tokens tb + 8*mi
+        const uint32_t src = dts + kr * DROW + mi * 16;
+#pragma unroll 4
+        for (int tb = 0; tb < TOK; tb += 32) {
+            uint32_t b[4];
+            ldmatrix_x4_trans(src + tb * 2, b);
 #pragma unroll
-        for (int v = 0; v < C / 8; ++v) {
-            const uint4 q = lds128(saddr + 16 * v);
-            const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int m = v * 8 + 2 * k;
-                float& lo = dv[REV ? C - 1 - m : m];
-                float& hi = dv[REV ? C - 2 - m : m + 1];
-                lo = fma_mixed<IN_T>((unsigned short)(qq[k] & 0xffffu), (unsigned short)w, lo);
-                hi = fma_mixed<IN_T>((unsigned short)(qq[k] >> 16), (unsigned short)w, hi);
+            for (int i = 0; i < 4; ++i) {
+                float d[4];
+                mma_k8<IN_T>(d, a_lo, b[i]);
+                sts_u32(out + (tb + 8 * i) * 2, pack2<IN_T>(d[0], d[1]));
             }
         }
     } else {
-        const float wf = __uint_as_float(w);
+        // matrices: (ranks 0..7, tokens tb..), (ranks 8..15, tokens tb..), (ranks 0..7, tokens tb+8..), (ranks 8..15, tokens tb+8..)
+        const uint32_t src = dts + (kr + 8 * (mi & 1)) * DROW + (mi >> 1) * 16;
+#pragma unroll 4
+        for (int tb = 0; tb < TOK; tb += 16) {
+            uint32_t b[4];
+            ldmatrix_x4_trans(src + tb * 2, b);
 #pragma unroll
-        for (int v = 0; v < C / 4; ++v) {
-            const uint4 q = lds128(saddr + 16 * v);
-            const float x[4] = {__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w)};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                float& d = dv[REV ? C - 1 - (v * 4 + k) : v * 4 + k];
-                d = fmaf(wf, x[k], d);
+            for (int i = 0; i < 2; ++i) {
+                float d[4];
+                mma_k16<IN_T>(d, a_lo, a_hi, b[2 * i], b[2 * i + 1]);
+                sts_u32(out + (tb + 8 * i) * 2, pack2<IN_T>(d[0], d[1]));
             }
         }
     }
-}
-
-__device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
-    return v;
 }
 
 template <int NST, typename IN_T, typename OUT_T, int C, bool HAS_Z, bool SOFTPLUS, bool REV, int NW, bool DTF>
@@ -388,21 +421,24 @@ __device__ __forceinline__ void lanes_consumer(const ScanParams& p, uint8_t* bas
     constexpr int TOK = Cfg::TOK, RCF = Cfg::RCF;
     constexpr bool FAST = SOFTPLUS && sizeof(IN_T) == 2;
     const int R = DTF ? (int)p.R : 0;
-    const int WB = Cfg::warp_bytes(R), AUX = Cfg::aux(R), RCW = Cfg::rcw(R);
+    const int WB = Cfg::warp_bytes(R);
     // everything below addresses shared memory through 32-bit shared-window addresses (LDS/STS, not generic LD/ST)
     const uint32_t ring = smem_u32(base) + warp * WB;
-    const uint32_t bcbuf = ring + Cfg::STAGES * Cfg::ITEM;
-    const uint32_t rcs = bcbuf + LN_BCS * AUX;
-    float* rc = reinterpret_cast<float*>(base + warp * WB + Cfg::STAGES * Cfg::ITEM + LN_BCS * AUX);
+    const uint32_t bcbuf = ring + LN_STAGES * Cfg::ITEM;
+    const uint32_t dts = bcbuf + LN_BCS * Cfg::BC;
+    const uint32_t dtile = dts + Cfg::dts_bytes(R);
+    const uint32_t rcs = dtile + (DTF ? Cfg::DTILE : 0);
+    float* rc = reinterpret_cast<float*>(base + warp * WB + (rcs - ring));
     const uint32_t full = smem_u32(base) + NW * WB + warp * Cfg::NBARS * 8;
-    const uint32_t empty = full + Cfg::STAGES * 8;
-    const uint32_t bcfull = empty + Cfg::STAGES * 8;
+    const uint32_t empty = full + LN_STAGES * 8;
+    const uint32_t bcfull = empty + LN_STAGES * 8;
     const uint32_t bcempty = bcfull + LN_BCS * 8;
+    const uint32_t dfull = bcempty + LN_BCS * 8;      // DTF only
+    const uint32_t dempty = dfull + 8;
 
-    // per-row constants {A[n]*s, bias*s', D, carry[n]}  (s = log2e, s' = 1 unless FAST: s = 1, s' = log2e), then the
-    // row's dt_proj weights (fused dt_proj): 16-bit weights packed two per word, zero-padded
+    // per-row constants {A[n]*s, bias*s', D, carry[n]}  (s = log2e, s' = 1 unless FAST: s = 1, s' = log2e)
     if (lane < w.nrows) {
-        float* k = rc + lane * RCW;
+        float* k = rc + lane * RCF;
 #pragma unroll
         for (int n = 0; n < NST; ++n) {
             k[n] = p.A[(w.d0 + lane) * NST + n] * (FAST ? 1.0f : kLog2e);
@@ -410,17 +446,16 @@ __device__ __forceinline__ void lanes_consumer(const ScanParams& p, uint8_t* bas
         }
         k[NST] = (p.bias ? p.bias[w.d0 + lane] : 0.0f) * (FAST ? kLog2e : 1.0f);
         k[NST + 1] = p.D ? p.D[w.d0 + lane] : 0.0f;
-        if constexpr (DTF) {
-            const IN_T* wr = (const IN_T*)p.wdt + (w.d0 + lane) * R;
-            uint32_t* kw = reinterpret_cast<uint32_t*>(k + RCF);
-            if constexpr (sizeof(IN_T) == 2) {
-                const unsigned short* ws = reinterpret_cast<const unsigned short*>(wr);
-                for (int q = 0; q < (R + 1) / 2; ++q)
-                    kw[q] = (uint32_t)ws[2 * q] | (2 * q + 1 < R ? (uint32_t)ws[2 * q + 1] << 16 : 0u);
-            } else {
-                for (int q = 0; q < R; ++q) kw[q] = __float_as_uint(to_f32(wr[q]));
-            }
-        }
+    }
+    uint32_t a_lo = 0, a_hi = 0;      // fused dt_proj: this lane's A fragments (row lane/4, ranks 2*(lane%4)+{0,1} [+8])
+    if constexpr (DTF) {
+        const int g = lane >> 2, k0 = 2 * (lane & 3);
+        const unsigned short* ws = reinterpret_cast<const unsigned short*>(p.wdt) + (w.d0 + g) * R;
+        auto wv = [&](int k) -> uint32_t { return (g < w.nrows && k < R) ? (uint32_t)ws[k] : 0u; };
+        a_lo = wv(k0) | (wv(k0 + 1) << 16);
+        a_hi = wv(k0 + 8) | (wv(k0 + 9) << 16);
+        // rank rows R .. rpad-1 of the dts_r tile are never written by the producer: zero them once (0 x stale NaN = NaN)
+        for (int q = R * Cfg::DROW + lane * 4; q < Cfg::dts_bytes(R); q += 128) sts_u32(dts + q, 0u);
     }
     __syncwarp();
 
@@ -437,10 +472,10 @@ __device__ __forceinline__ void lanes_consumer(const ScanParams& p, uint8_t* bas
         const int64_t tok0 = (int64_t)step * TOK + lane * C;       // first scan-order token of this lane
         const bool full_step = (int64_t)(step + 1) * TOK <= p.L;
         const int nv = full_step ? C : (int)max((int64_t)0, min((int64_t)C, p.L - tok0));
-        const int bs = step % LN_BCS;
         if (r == 0) {
+            const int bs = step % LN_BCS;
             mbar_wait_s(bcfull + bs * 8, (uint32_t)(step / LN_BCS) & 1u);
-            const uint32_t bc = bcbuf + bs * AUX + lane_off;
+            const uint32_t bc = bcbuf + bs * Cfg::BC + lane_off;
 #pragma unroll
             for (int n = 0; n < NST; ++n) {
                 lds_tokens<IN_T, C, REV>(bc + n * Cfg::CHUNK, Bv[n]);
@@ -451,59 +486,34 @@ __device__ __forceinline__ void lanes_consumer(const ScanParams& p, uint8_t* bas
                     if (!full_step && j >= nv) { Bv[n][j] = 0.0f; Cv[n][j] = 0.0f; }   // stale smem may hold NaN/Inf
                 }
             }
-            if constexpr (!DTF) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive_s(bcempty + bs * 8);
+            if constexpr (DTF) {
+                // the step's delta tile for all rows of the warp (the previous step's tile was drained before the
+                // __syncwarp of its last item)
+                mbar_wait_s(dfull, (uint32_t)step & 1u);
+                dt_tile_mma<IN_T, TOK, Cfg::DROW>(dts, dtile, a_lo, a_hi, R > 8, lane);
                 __syncwarp();
-                if (lane == 0) mbar_arrive_s(bcempty + bs * 8);
+                if (lane == 0) mbar_arrive_s(dempty);
             }
         }
         mbar_wait_s(full + slot * 8, phase);
         const uint32_t item = ring + slot * Cfg::ITEM + lane_off;
         float uv[C], dv[C], zv[HAS_Z ? C : 1];
         lds_tokens<IN_T, C, REV>(item, uv);
-        if constexpr (!DTF) lds_tokens<IN_T, C, REV>(item + Cfg::CHUNK, dv);
+        if constexpr (DTF) lds_tokens<IN_T, C, REV>(dtile + r * Cfg::DROW + lane_off, dv);
+        else lds_tokens<IN_T, C, REV>(item + Cfg::CHUNK, dv);
         if constexpr (HAS_Z) lds_tokens<IN_T, C, REV>(item + Cfg::ZOFF, zv);
         float kc[RCF];
 #pragma unroll
         for (int q = 0; q < RCF / 4; ++q) {
-            const uint4 t = lds128(rcs + (r * RCW + 4 * q) * 4);
+            const uint4 t = lds128(rcs + (r * RCF + 4 * q) * 4);
             kc[4 * q] = __uint_as_float(t.x); kc[4 * q + 1] = __uint_as_float(t.y);
             kc[4 * q + 2] = __uint_as_float(t.z); kc[4 * q + 3] = __uint_as_float(t.w);
         }
         __syncwarp();                                    // every lane has drained the slot (and read the row table)
         if (lane == 0) mbar_arrive_s(empty + slot * 8);  // hand it back to the producer
-        if (++slot == Cfg::STAGES) { slot = 0; phase ^= 1u; }
-
-        if constexpr (DTF) {
-            // fused dt_proj: delta[token] = sum_r w[row, r] * dts_r[r, token]; the rank rows sit in the step's aux buffer
-            const uint32_t xr = bcbuf + bs * AUX + 2 * NST * Cfg::CHUNK + lane_off;
-            const uint32_t wr = rcs + (r * RCW + RCF) * 4;
-#pragma unroll
-            for (int j = 0; j < C; ++j) dv[j] = 0.0f;
-            // XPoint's ranks (dt_rank = d_model / 16 = 6, 12) are fully unrolled so that the rank rows' LDS run ahead of
-            // the FMAs; other ranks take the rolled loop
-            auto rank_rows = [&](auto rr_tag) {
-                constexpr int RR = decltype(rr_tag)::value;      // 0 = runtime rank
-                const int Rn = RR ? RR : R;
-                if constexpr (sizeof(IN_T) == 2) {
-#pragma unroll(RR ? 16 : 1)
-                    for (int q = 0; q < Rn; q += 2) {
-                        const uint32_t w2 = lds32(wr + 2 * q);
-                        dt_accumulate<IN_T, C, REV>(xr + q * Cfg::CHUNK, w2 & 0xffffu, dv);
-                        if (q + 1 < Rn) dt_accumulate<IN_T, C, REV>(xr + (q + 1) * Cfg::CHUNK, w2 >> 16, dv);
-                    }
-                } else {
-#pragma unroll(RR ? 16 : 1)
-                    for (int q = 0; q < Rn; ++q) dt_accumulate<IN_T, C, REV>(xr + q * Cfg::CHUNK, lds32(wr + 4 * q), dv);
-                }
-            };
-            if (R == 6) rank_rows(std::integral_constant<int, 6>{});
-            else if (R == 12) rank_rows(std::integral_constant<int, 12>{});
-            else rank_rows(std::integral_constant<int, 0>{});
-            if (r == w.nrows - 1) {                      // last row of the step: the aux buffer is free again
-                __syncwarp();
-                if (lane == 0) mbar_arrive_s(bcempty + bs * 8);
-            }
-        }
+        if (++slot == LN_STAGES) { slot = 0; phase ^= 1u; }
 
         const float kb = kc[NST], kD = kc[NST + 1];
         auto body = [&](auto full_tag) {
@@ -547,7 +557,7 @@ __device__ __forceinline__ void lanes_consumer(const ScanParams& p, uint8_t* bas
                 const float hin = fmaf(Pe, hc, Se);
 #pragma unroll
                 for (int j = 0; j < C; ++j) y[j] = fmaf(fmaf(pl[j], hin, hl[j]), Cv[n][j], y[j]);
-                if (lane == 31) sts32(rcs + (r * RCW + NST + 2 + n) * 4, fmaf(P, hc, S_));
+                if (lane == 31) sts32(rcs + (r * RCF + NST + 2 + n) * 4, fmaf(P, hc, S_));
             }
             if constexpr (HAS_Z) {
 #pragma unroll
@@ -562,7 +572,7 @@ __device__ __forceinline__ void lanes_consumer(const ScanParams& p, uint8_t* bas
     __syncwarp();
     if (p.last && lane < w.nrows) {
 #pragma unroll
-        for (int n = 0; n < NST; ++n) p.last[(w.b * p.dim + w.d0 + lane) * NST + n] = rc[lane * RCW + NST + 2 + n];
+        for (int n = 0; n < NST; ++n) p.last[(w.b * p.dim + w.d0 + lane) * NST + n] = rc[lane * RCF + NST + 2 + n];
     }
 }
 
@@ -873,9 +883,11 @@ static int launch_lanes_cfg(const ScanParams& p, int64_t warps, cudaStream_t st)
 
 template <int NST, typename IN_T, typename OUT_T, int C> static int launch_lanes_c(const ScanParams& p, int64_t warps, cudaStream_t st) {
     constexpr int NW = 4;
-    if (p.R > 0) {      // fused dt_proj (no z gate on this path: lanes_supports_dt)
-        return p.softplus ? launch_lanes_cfg<NST, IN_T, OUT_T, C, false, true, NW, true>(p, warps, st)
-                          : launch_lanes_cfg<NST, IN_T, OUT_T, C, false, false, NW, true>(p, warps, st);
+    if constexpr (sizeof(IN_T) == 2) {
+        if (p.R > 0) {      // fused dt_proj (16-bit inputs, no z gate: lanes_supports_dt)
+            return p.softplus ? launch_lanes_cfg<NST, IN_T, OUT_T, C, false, true, NW, true>(p, warps, st)
+                              : launch_lanes_cfg<NST, IN_T, OUT_T, C, false, false, NW, true>(p, warps, st);
+        }
     }
     if (p.z) {
         return p.softplus ? launch_lanes_cfg<NST, IN_T, OUT_T, C, true, true, NW, false>(p, warps, st)
@@ -885,8 +897,10 @@ template <int NST, typename IN_T, typename OUT_T, int C> static int launch_lanes
                       : launch_lanes_cfg<NST, IN_T, OUT_T, C, false, false, NW, false>(p, warps, st);
 }
 
-constexpr int LN_MAX_DT_RANK = 16;   // fused dt_proj on the lanes kernel (larger ranks: the aux buffers outgrow shared memory)
-static bool lanes_supports_dt(const ScanParams& p) { return p.R <= LN_MAX_DT_RANK && !p.z; }
+constexpr int LN_MAX_DT_RANK = 16;   // fused dt_proj on the lanes kernel: one m16n8k8 / m16n8k16 MMA along the rank
+template <typename IN_T> static bool lanes_supports_dt(const ScanParams& p) {
+    return sizeof(IN_T) == 2 && p.R <= LN_MAX_DT_RANK && !p.z;
+}
 
 template <int NST, typename IN_T, typename OUT_T> static int launch_lanes(ScanParams p, cudaStream_t st) {
     const int64_t Dg = p.dim / p.groups;
@@ -901,8 +915,9 @@ template <int NST, typename IN_T, typename OUT_T> static int launch_lanes(ScanPa
     static const int c_override = env_int("XP_LANES_C", 0);   // tuning knob: 8 | 16
     if constexpr (NST == 1 && sizeof(IN_T) == 2) {
         const bool pads_more = ceil_div(p.L, 512) * 512 > ceil_div(p.L, 256) * 256;
-        // fused dt_proj: the R rank rows live in the aux buffers; keep at least two CTAs per SM
-        const bool too_big = p.R > 0 && LanesCfg<NST, IN_T, 16, false, 4, true>::smem((int)p.R) > 110 * 1024;
+        // fused dt_proj: the dts_r / delta tiles grow with the step; keep at least two CTAs per SM
+        static const int dt_c16 = env_int("XP_LANES_DT_C16", 0);   // measured: 256-token steps (4 CTAs/SM) beat 512-token steps (2 CTAs/SM)
+        const bool too_big = p.R > 0 && (LanesCfg<NST, IN_T, 16, false, 4, true>::smem((int)p.R) > 110 * 1024 || !dt_c16);
         if (c_override == 16 || (c_override != 8 && !pads_more && !too_big)) return launch_lanes_c<NST, IN_T, OUT_T, 16>(p, warps, st);
     }
     return launch_lanes_c<NST, IN_T, OUT_T, 8>(p, warps, st);
@@ -969,7 +984,7 @@ template <typename IN_T, typename OUT_T> static int dispatch(const ScanParams& p
     vec_ok = vec_ok && (p.o_bs % vo == 0) && (p.o_ds % vo == 0);
     vec_ok = vec_ok && (p.u_gs % va == 0);
     if (p.R > 0) {            // fused dt_proj: lanes kernel or the generic kernel
-        vec_ok = vec_ok && p.dl_gs % va == 0 && lanes_supports_dt(p);
+        vec_ok = vec_ok && p.dl_gs % va == 0 && lanes_supports_dt<IN_T>(p);
         if (vec_ok && p.dstate == 1) return launch_lanes<1, IN_T, OUT_T>(p, st);
         if (vec_ok && p.dstate == 2) return launch_lanes<2, IN_T, OUT_T>(p, st);
         return launch_generic<IN_T, OUT_T>(p, st);

@@ -51,6 +51,68 @@ def normalize_descriptors(x: torch.Tensor, channel_last_copy: bool = False):
     return (out, out_cl) if channel_last_copy else out
 
 
+def detector_post_rows(logits_rows: torch.Tensor, B: int, Hc: int, Wc: int, r: int = 8) -> torch.Tensor:
+    """detector_post on channel-last rows: logits_rows (B*Hc*Wc, ld) with the r*r+1 logits of a cell first in its row
+    (ld >= r*r+1; the model's 1x1-convolution GEMM writes 72-wide rows) -> (B, 1, r*Hc, r*Wc) fp32."""
+    dev = _lib.require_cuda(logits_rows)
+    if logits_rows.dim() != 2 or logits_rows.shape[0] != B * Hc * Wc or logits_rows.stride(1) != 1:
+        raise RuntimeError("detector_post_rows: expected (B*Hc*Wc, ld) rows with unit column stride")
+    if logits_rows.shape[1] < r * r + 1:
+        raise RuntimeError(f"detector_post_rows: rows must hold at least {r * r + 1} logits")
+    prob = torch.empty((B, 1, Hc * r, Wc * r), dtype=torch.float32, device=dev)
+    if prob.numel():
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().xp_detector_post_cl(_lib.ptr(logits_rows), _lib.ptr(prob), B, Hc, Wc, r, logits_rows.stride(0),
+                                                      _lib.dtype_code(logits_rows), _lib.stream_ptr(dev)))
+        _lib.count_launches(1)
+    return prob
+
+
+def normalize_descriptor_rows(x_rows: torch.Tensor, B: int, Hc: int, Wc: int, want_channel_first: bool = True):
+    """F.normalize over the channels of channel-last rows x_rows (B*Hc*Wc, C).  Returns (desc (B, C, Hc, Wc) fp32 or None,
+    desc_cl (B, Hc, Wc, C) fp32)."""
+    dev = _lib.require_cuda(x_rows)
+    x_rows = x_rows.contiguous()
+    C = x_rows.shape[1]
+    if x_rows.dim() != 2 or x_rows.shape[0] != B * Hc * Wc:
+        raise RuntimeError("normalize_descriptor_rows: expected (B*Hc*Wc, C) rows")
+    out = torch.empty((B, C, Hc, Wc), dtype=torch.float32, device=dev) if want_channel_first else None
+    out_cl = torch.empty((B, Hc, Wc, C), dtype=torch.float32, device=dev)
+    if out_cl.numel():
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().xp_l2_normalize_cl(_lib.ptr(x_rows), _lib.ptr(out), _lib.ptr(out_cl), B, C, Hc * Wc,
+                                                     _lib.dtype_code(x_rows), _lib.stream_ptr(dev)))
+        _lib.count_launches(1)
+    return out, out_cl
+
+
+def encoder_tail(x: torch.Tensor, pend, bs: int = 4, pad_dtype=None, want_encoder_output: bool = True):
+    """x (B, H, W, C) fp32 channel-last residual stream [+ pend] -> depth_to_space(bs) (VMamba.py:1500-1505):
+    (encoder_output (B, C/bs^2, H*bs, W*bs) fp32 or None, ReflectionPad2d(1) of it as a channels-last tensor of
+    pad_dtype viewed (B, C/bs^2, H*bs+2, W*bs+2) or None)."""
+    dev = _lib.require_cuda(x, pend)
+    x = x.contiguous()
+    pend = None if pend is None else pend.contiguous()
+    B, H, W, Cn = x.shape
+    CO = Cn // (bs * bs)
+    enc = torch.empty((B, CO, H * bs, W * bs), dtype=torch.float32, device=dev) if want_encoder_output else None
+    padded = None
+    if pad_dtype is not None:
+        padded = torch.empty((B, H * bs + 2, W * bs + 2, CO), dtype=pad_dtype, device=dev)
+    if B:
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().xp_encoder_tail(_lib.ptr(x), _lib.ptr(pend), _lib.ptr(enc), _lib.ptr(padded), B, H, W, CO, bs,
+                                                  _lib.dtype_code(x), 0 if pend is None else _lib.dtype_code(pend),
+                                                  0 if padded is None else _lib.dtype_code(padded), _lib.stream_ptr(dev)))
+        _lib.count_launches(1)
+    return enc, (None if padded is None else padded.permute(0, 3, 1, 2))
+
+
+def encoder_tail_supported(x: torch.Tensor, bs: int = 4) -> bool:
+    return x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[3] % (bs * bs) == 0 and \
+        x.shape[3] // (bs * bs) in (8, 16, 32, 48, 64) and x.shape[1] * bs >= 3 and x.shape[2] * bs >= 3
+
+
 # ------------------------------------------------------------------------------------------ NMS
 class Keypoints(NamedTuple):
     prob_nms: Optional[torch.Tensor]   # (B, H, W) fp32 or None

@@ -12,6 +12,8 @@ library call; stays a library call"): the dense projections / convolutions / Lay
 """
 from __future__ import annotations
 
+import os
+
 import math
 from collections import OrderedDict
 from functools import partial
@@ -250,7 +252,7 @@ class SS2D(nn.Module):
         w = self._fused_weights(B, xx.dtype)
         x_dbl = torch.matmul(w["wx"], xx)                                          # (B, 2, 2(R+2N), L)
         x_dbl = x_dbl.view(B, K, R + 2 * N, L)
-        if N <= 2 and R <= 16 and L % 8 == 0 and not getattr(self, "disable_dt_fusion", False):
+        if (N <= 2 and R <= 16 and L % 8 == 0 and xx.dtype != torch.float32 and getattr(self, "fuse_dt_proj", FUSE_DT_PROJ)):
             # the scan forms delta = W_dt x dts_r itself, the (B, K*D, L) delta never reaches HBM
             ys, _ = scan_forward(xx.view(B, 2 * D, L), x_dbl[:, :, :R], w["A"], x_dbl[:, :, R:R + N], x_dbl[:, :, R + N:],
                                  w["Ds"], None, w["dt_bias"], True, True, u_group_div=2,
@@ -304,6 +306,13 @@ class SS2D(nn.Module):
             if zact is not None:
                 y = y * zact
         return self.out_proj(y)
+
+
+# SURVEY 8f row f1 (fused dt_proj, xp_scan_args.dt_weight) is built, parity-tested and measured, but it is NOT the default:
+# the N=1 scan kernel is bound by instruction issue / latency as much as by HBM, so dropping the delta stream (-25 % bytes)
+# buys 0.3 ms per stage-0 block against dt_proj + scan while the kernel's bytes/s falls.
+# XP_FUSE_DT_PROJ=1 or `module.fuse_dt_proj = True` turns it on.
+FUSE_DT_PROJ = os.environ.get("XP_FUSE_DT_PROJ", "0") not in ("", "0")
 
 
 class VSSBlock(nn.Module):  # VMamba.py:1153-1240
@@ -484,15 +493,20 @@ class VSSM(nn.Module):
                               pre_bias=conv.bias, want_sum=False)
         return y
 
-    def forward(self, x):
+    def forward_features(self, x):
+        """Everything up to the last residual add: returns (x, pend) channel-last with the stage output = x + pend."""
         x = self._patch_embed(x)
+        pend = None
         for i, layer in enumerate(self.layers):
             x, pend = self._run_blocks(layer.blocks, x)
-            if isinstance(layer.downsample, nn.Identity):
-                if pend is not None:
-                    x = x + pend
-            else:
-                x = self._downsample(layer.downsample, x, pend)
+            if not isinstance(layer.downsample, nn.Identity):
+                x, pend = self._downsample(layer.downsample, x, pend), None
+        return x, pend
+
+    def forward(self, x):
+        x, pend = self.forward_features(x)
+        if pend is not None:
+            x = x + pend
         return self.depth_to_space(x.permute(0, 3, 1, 2), 4)
 
 

@@ -165,12 +165,19 @@ class XPoint(nn.Module):
         with torch.no_grad():
             w1d, b1d, w2d, b2d = fold(self.detector_head_convolutions)
             w1s, b1s, w2s, b2s = fold(self.descriptor_head_convolutions)
+            # the 65-wide detector GEMM is padded to 72 columns (16-byte rows for 16-bit outputs, aligned cuBLAS kernels)
+            npad = (-w2d.shape[0]) % 8
+            w2d_p = torch.cat([w2d, w2d.new_zeros(npad, w2d.shape[1])]) if npad else w2d
+            b2d_p = torch.cat([b2d, b2d.new_zeros(npad)]) if npad else b2d
             folded = dict(w1=torch.cat([w1d, w1s]).contiguous(memory_format=torch.channels_last), b1=torch.cat([b1d, b1s]),
-                          w2_det=w2d.t().contiguous(), b2_det=b2d, w2_desc=w2s.t().contiguous(), b2_desc=b2s, n1=w1d.shape[0])
+                          w2_det=w2d_p.t().contiguous(), b2_det=b2d_p, w2_desc=w2s.t().contiguous(), b2_desc=b2s,
+                          n1=w1d.shape[0], n_det=w2d.shape[0])
         self._head_cache = (key, folded)
         return folded
 
-    def _heads_fused(self, x):
+    def _heads_fused(self, x, padded=None, want_desc=True):
+        """x (B, C, Hc, Wc) encoder output; ``padded``: its ReflectionPad2d(1) already in the compute dtype and
+        channels-last (xp_encoder_tail), else it is formed here.  Returns prob, logits, desc, desc_cl."""
         f32w = self._folded_heads()
         cdt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
         f = f32w.get(cdt)
@@ -179,7 +186,10 @@ class XPoint(nn.Module):
             f["w1"] = f["w1"].contiguous(memory_format=torch.channels_last)
             f32w[cdt] = f
         Bn, _, Hc, Wc = x.shape
-        xp = self.detector_head_convolutions[0](x).to(dtype=cdt, memory_format=torch.channels_last)   # pad once for both heads
+        if padded is not None and padded.dtype == cdt:
+            xp = padded
+        else:
+            xp = self.detector_head_convolutions[0](x).to(dtype=cdt, memory_format=torch.channels_last)   # pad once for both heads
         y = None
         if not getattr(self, "_no_cudnn_relu", False):
             try:                                 # cuDNN's fused conv + bias + ReLU
@@ -190,28 +200,37 @@ class XPoint(nn.Module):
             y = torch.relu_(nn.functional.conv2d(xp, f["w1"], f["b1"]))
         y = y.permute(0, 2, 3, 1).reshape(-1, y.shape[1])                                            # (rows, 512) channel-last
         n1 = f["n1"]
-        logits = torch.addmm(f["b2_det"], y[:, :n1], f["w2_det"])                                    # (rows, 65)
+        logits = torch.addmm(f["b2_det"], y[:, :n1], f["w2_det"])                                    # (rows, 72), 65 used
         draw = torch.addmm(f["b2_desc"], y[:, n1:], f["w2_desc"])                                    # (rows, 256)
-        logits = logits.view(Bn, Hc, Wc, -1).permute(0, 3, 1, 2).contiguous()
-        draw = draw.view(Bn, Hc, Wc, -1).permute(0, 3, 1, 2).contiguous()
+        # the channel-last GEMM outputs are consumed where they lie (no (B, C, Hc, Wc) permute copies)
         if self.config["force_return_logits"]:
-            prob, lg = None, logits.to(torch.float)
+            prob = None
+            lg = logits[:, :f["n_det"]].reshape(Bn, Hc, Wc, -1).permute(0, 3, 1, 2).contiguous().to(torch.float)
         else:
-            prob, lg = pp.detector_post(logits, self.encoder_downsample_ratio), None
-        desc, desc_cl = pp.normalize_descriptors(draw, channel_last_copy=True)
+            prob, lg = pp.detector_post_rows(logits, Bn, Hc, Wc, self.encoder_downsample_ratio), None
+        desc, desc_cl = pp.normalize_descriptor_rows(draw, Bn, Hc, Wc, want_channel_first=want_desc)
         return prob, lg, desc, desc_cl
 
-    def forward_impl(self, data):  # XPoint.py:283-323
-        x = self.encoder(data["image"])
+    def forward_impl(self, data, want_desc=True):  # XPoint.py:283-323
         out = {"prob": None, "logits": None}
-        encoder_output = x.clone().detach()
         if self._heads_foldable():
+            # residual add -> depth_to_space -> clone -> reflection pad -> compute dtype in ONE pass (xp_encoder_tail)
+            xf, pend = self.encoder.forward_features(data["image"])
+            cdt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else torch.float32
+            if pp.encoder_tail_supported(xf):
+                encoder_output, padded = pp.encoder_tail(xf, pend, 4, pad_dtype=cdt)
+            else:
+                x = self.encoder.depth_to_space((xf if pend is None else xf + pend).permute(0, 3, 1, 2), 4)
+                encoder_output, padded = x, None
             # desc_cl: the same unit descriptors as (B, Hc, Wc, 256) -- the layout the sampler gathers 1 KiB rows from
-            out["prob"], out["logits"], out["desc"], out["desc_cl"] = self._heads_fused(x)
-        else:
-            out["prob"], out["logits"] = self.detector_head(x)
-            if self.config["descriptor_head"]:
-                out["desc"] = self.descriptor_head(x)
+            out["prob"], out["logits"], out["desc"], out["desc_cl"] = self._heads_fused(encoder_output, padded, want_desc)
+            out["encoder_output"] = encoder_output
+            return out
+        x = self.encoder(data["image"])
+        encoder_output = x.clone().detach()
+        out["prob"], out["logits"] = self.detector_head(x)
+        if self.config["descriptor_head"]:
+            out["desc"] = self.descriptor_head(x)
         out["encoder_output"] = encoder_output
         return out
 
@@ -224,13 +243,17 @@ class XPoint(nn.Module):
             pred_thermal = self.forward_impl(data["thermal"])
             return pred_optical, pred_thermal, None
 
-    def forward_pair_batched(self, optical: torch.Tensor, thermal: torch.Tensor):
+    def forward_pair_batched(self, optical: torch.Tensor, thermal: torch.Tensor, want_desc=True, split=True):
         """Same weights serve both spectra (multispectral=False), so the two encoder passes of XPoint.forward
-        (XPoint.py:187-188) run as one 2B batch.  Returns (pred_optical, pred_thermal) dicts."""
+        (XPoint.py:187-188) run as one 2B batch.  Returns (pred_optical, pred_thermal) dicts, or with ``split=False`` the
+        single dict of the 2B batch (optical first); ``want_desc=False`` skips the channel-first descriptor map when
+        only the channel-last copy is consumed."""
         Bn = optical.shape[0]
         ctx = torch.autocast("cuda", dtype=torch.float16) if self.config["mixed_precision"] else contextlib.nullcontext()
         with ctx:
-            out = self.forward_impl({"image": torch.cat([optical, thermal], 0)})
+            out = self.forward_impl({"image": torch.cat([optical, thermal], 0)}, want_desc=want_desc)
+        if not split:
+            return out
         first = {k: (v[:Bn] if v is not None else None) for k, v in out.items()}
         second = {k: (v[Bn:] if v is not None else None) for k, v in out.items()}
         return first, second
@@ -261,12 +284,15 @@ class PairPipeline:
     def tail(self, prob_o, prob_t, desc_o, desc_t, channel_last=False) -> PairResult:
         """prob (B,1,H,W) fp32; desc (B,256,Hc,Wc) fp32 [or (B,Hc,Wc,256) with channel_last] -> keypoints, descriptors
         and mutual matches."""
-        B, _, H, W = prob_o.shape
-        prob = torch.cat([prob_o, prob_t], 0).reshape(2 * B, H, W)
+        return self.tail_batched(torch.cat([prob_o, prob_t], 0), torch.cat([desc_o, desc_t], 0), channel_last)
+
+    def tail_batched(self, prob, desc, channel_last=False) -> PairResult:
+        """The same on the 2B batch the encoder produced (optical images first, then thermal): no concatenation."""
+        B, H, W = prob.shape[0] // 2, prob.shape[-2], prob.shape[-1]
+        prob = prob.reshape(2 * B, H, W)
         kps = pp.nms_keypoints(prob, self.nms, self.thr, self.iou, self.topk, kp_threshold=self.thr, capacity=self.topk,
                                want_map=False)
         count = torch.clamp(kps.count, max=self.topk)
-        desc = torch.cat([desc_o, desc_t], 0)
         d = pp.sample_descriptors(kps.keypoints, count, desc, H, W, channel_last)
         m = pp.mnn_match(d[:B], d[B:], count[:B], count[B:], use_tensor_cores=self.use_tensor_cores)
         return PairResult(kps.keypoints[:B], kps.keypoints[B:], count[:B], count[B:], d[:B], d[B:], m.match_idx,
@@ -274,7 +300,7 @@ class PairPipeline:
 
     @torch.no_grad()
     def __call__(self, optical: torch.Tensor, thermal: torch.Tensor) -> PairResult:
-        po, pt = self.net.forward_pair_batched(optical, thermal)
-        if po.get("desc_cl") is not None:
-            return self.tail(po["prob"], pt["prob"], po["desc_cl"], pt["desc_cl"], channel_last=True)
-        return self.tail(po["prob"], pt["prob"], po["desc"], pt["desc"])
+        out = self.net.forward_pair_batched(optical, thermal, want_desc=False, split=False)
+        if out.get("desc_cl") is not None:
+            return self.tail_batched(out["prob"], out["desc_cl"], channel_last=True)
+        return self.tail_batched(out["prob"], out["desc"])

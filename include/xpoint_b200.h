@@ -170,9 +170,10 @@ XP_API int xp_ss2d_pack(const void* x, void* xx, int64_t B, int64_t D, int64_t H
 XP_API int xp_ss2d_dwconv_pack(const void* in, const float* weight, const float* bias, void* xx, int64_t B, int64_t D,
                                int64_t H, int64_t W, int64_t in_token_stride, int32_t dtype, int32_t silu,
                                xp_stream_t stream);
- /* xp_ss2d_dt_proj: delta (B, G, D, L) = weight (G, D, R) fp32 x dts_r (B, G, R, L), R = dt_rank <= 8: the dt_proj of
- * SS2D (VMamba.py:607-608, :325) as a store-bound outer product.  dts_r is a strided view of the x_proj output
- * (element strides given); delta is contiguous, in the dtype of dts_r. */
+ /* xp_ss2d_dt_proj: delta (B, G, D, L) = weight (G, D, R) fp32 x dts_r (B, G, R, L): the dt_proj of SS2D (VMamba.py:607-608,
+ * :325) as a store-bound outer product.  R = dt_rank <= 8 for any dtype; 9..16 for 16-bit inputs (weights rounded to the
+ * input dtype as under autocast, mixed-precision FMA with fp32 accumulation).  dts_r is a strided view of the x_proj
+ * output (element strides given); delta is contiguous, in the dtype of dts_r. */
 XP_API int xp_ss2d_dt_proj(const void* dts_r, const float* weight, void* delta, int64_t B, int64_t G, int64_t D, int64_t R,
                            int64_t L, int64_t x_batch_stride, int64_t x_group_stride, int64_t x_rank_stride, int32_t dtype,
                            xp_stream_t stream);

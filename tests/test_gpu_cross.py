@@ -250,6 +250,18 @@ def test_patch_embed_stem_vs_torch(cin, C1, H, W, odt):
 @pytest.mark.parametrize("B,G,D,R,N,L", [(2, 4, 96, 6, 1, 1280), (1, 4, 24, 3, 2, 328), (3, 2, 40, 8, 4, 64), (1, 4, 16, 1, 1, 24)])
 def test_ss2d_dt_proj_vs_torch(dtype, tol, B, G, D, R, N, L):
     """dt_proj of SS2D (VMamba.py:607-608) on a strided view of the x_proj output."""
+    _dt_proj_case(dtype, tol, B, G, D, R, N, L)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 2e-3), (torch.bfloat16, 1.6e-2)])
+@pytest.mark.parametrize("B,G,D,R,N,L", [(2, 4, 192, 12, 1, 1280), (1, 4, 40, 9, 2, 328), (2, 2, 24, 16, 1, 64), (1, 4, 136, 13, 1, 520)])
+def test_ss2d_dt_proj_rank_9_to_16(dtype, tol, B, G, D, R, N, L):
+    """Ranks 9..16 (XPoint stage 1: dt_rank 12) take the mixed-precision-FMA kernel; weights are rounded to the input dtype
+    as the reference's autocast GEMM does."""
+    _dt_proj_case(dtype, tol, B, G, D, R, N, L)
+
+
+def _dt_proj_case(dtype, tol, B, G, D, R, N, L):
     from xpoint_b200 import ss2d
     g = torch.Generator().manual_seed(R + L)
     x_dbl = torch.randn(B, G, R + 2 * N, L, generator=g).to(dtype).to(DEV)

@@ -396,6 +396,71 @@ __global__ void __launch_bounds__(256) ss2d_dt_proj_kernel(const T* __restrict__
     }
 }
 
+// 16-bit inputs with ranks 9..16 (stage 1 of XPoint: dt_rank 12): the 8 tokens x R rank rows of a thread stay PACKED (16-byte
+// vectors, R * 4 registers) and feed the mixed-precision FMA of sm_100 (fma.rn.f32.f16 -> FHFMA: 16-bit operands taken
+// from either half of a register, fp32 accumulator, full FFMA rate), so nothing is widened; the (D, R) weights of the
+// group are rounded to the input dtype (what the reference's autocast GEMM multiplies with) and paired in shared memory.
+template <typename T> __device__ __forceinline__ float fma_mixed16(uint32_t a16, uint32_t b16, float acc);
+template <> __device__ __forceinline__ float fma_mixed16<__half>(uint32_t a16, uint32_t b16, float acc) {
+    float d;
+    asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"((unsigned short)a16), "h"((unsigned short)b16), "f"(acc));
+    return d;
+}
+template <> __device__ __forceinline__ float fma_mixed16<__nv_bfloat16>(uint32_t a16, uint32_t b16, float acc) {
+    float d;
+    asm("fma.rn.f32.bf16 %0, %1, %2, %3;" : "=f"(d) : "h"((unsigned short)a16), "h"((unsigned short)b16), "f"(acc));
+    return d;
+}
+
+template <typename T, int RP>     // RP: rank pairs held per thread (8 -> ranks up to 16)
+__global__ void __launch_bounds__(256) ss2d_dt_proj16_kernel(const T* __restrict__ xr, const float* __restrict__ Wt,
+                                                             T* __restrict__ out, int G, int D, int R, int64_t L, int64_t x_bs,
+                                                             int64_t x_gs, int64_t x_rs) {
+    extern __shared__ uint32_t wsm[];                  // [D][RP] weight pairs (W[d][2q], W[d][2q+1]) in T, zero-padded
+    const int tg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int64_t bg = blockIdx.y;
+    const int64_t b = bg / G, g = bg % G;
+    const float* Wg = Wt + g * (int64_t)D * R;
+    for (int i = threadIdx.x; i < D * RP; i += 256) {
+        const int d = i / RP, q = i % RP;
+        const T lo = from_f32<T>(2 * q < R ? Wg[(int64_t)d * R + 2 * q] : 0.0f);
+        const T hi = from_f32<T>(2 * q + 1 < R ? Wg[(int64_t)d * R + 2 * q + 1] : 0.0f);
+        wsm[i] = (uint32_t)*reinterpret_cast<const unsigned short*>(&lo) |
+                 ((uint32_t)*reinterpret_cast<const unsigned short*>(&hi) << 16);
+    }
+    __syncthreads();
+    const int64_t l0 = ((int64_t)blockIdx.x * 32 + tg) * 8;
+    if (l0 >= L) return;                               // L % 8 == 0: token groups are all-or-nothing
+    uint4 x[2 * RP];
+    const T* src = xr + b * x_bs + g * x_gs + l0;
+#pragma unroll
+    for (int r = 0; r < 2 * RP; ++r) x[r] = r < R ? __ldg(reinterpret_cast<const uint4*>(src + r * x_rs)) : make_uint4(0u, 0u, 0u, 0u);
+    T* dst = out + (bg * D) * L + l0;
+    for (int d = rl; d < D; d += 8) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+#pragma unroll
+        for (int q = 0; q < RP; ++q) {
+            const uint32_t w2 = wsm[d * RP + q];       // broadcast
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t w = h ? w2 >> 16 : w2 & 0xffffu;
+                const uint4 v = x[2 * q + h];
+                acc[0] = fma_mixed16<T>(v.x & 0xffffu, w, acc[0]); acc[1] = fma_mixed16<T>(v.x >> 16, w, acc[1]);
+                acc[2] = fma_mixed16<T>(v.y & 0xffffu, w, acc[2]); acc[3] = fma_mixed16<T>(v.y >> 16, w, acc[3]);
+                acc[4] = fma_mixed16<T>(v.z & 0xffffu, w, acc[4]); acc[5] = fma_mixed16<T>(v.z >> 16, w, acc[5]);
+                acc[6] = fma_mixed16<T>(v.w & 0xffffu, w, acc[6]); acc[7] = fma_mixed16<T>(v.w >> 16, w, acc[7]);
+            }
+        }
+        uint4 raw;
+        T* e = reinterpret_cast<T*>(&raw);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e[j] = from_f32<T>(acc[j]);
+        *reinterpret_cast<uint4*>(dst + (int64_t)d * L) = raw;
+    }
+}
+
 template <typename TO, int TH, int TW, int DPER>
 static int merge_norm_launch_d(const float* ys, const float* gamma, const float* beta, const void* zact, void* out, int64_t B,
                                int64_t D, int64_t H, int64_t W, float eps, cudaStream_t st) {
@@ -504,7 +569,8 @@ extern "C" int xp_ss2d_dt_proj(const void* dts_r, const float* weight, void* del
                                xp_stream_t stream) {
     XP_REQUIRE(dts_r && weight && delta, "xp_ss2d_dt_proj: NULL tensor pointer");
     XP_REQUIRE(B >= 0 && G > 0 && D > 0 && L > 0, "xp_ss2d_dt_proj: bad shape");
-    XP_REQUIRE(R >= 1 && R <= 8, "xp_ss2d_dt_proj: dt_rank must be in 1..8 (got %lld)", (long long)R);
+    XP_REQUIRE(R >= 1 && (R <= 8 || (R <= 16 && dtype != XP_F32 && D * 8 * 4 <= 48 * 1024)),
+               "xp_ss2d_dt_proj: dt_rank must be in 1..8, or 9..16 with 16-bit inputs and D <= 1536 (got %lld)", (long long)R);
     XP_REQUIRE(dtype >= XP_F32 && dtype <= XP_BF16, "xp_ss2d_dt_proj: unsupported dtype %d", dtype);
     const int64_t vec = dtype == XP_F32 ? 4 : 8;
     XP_REQUIRE(L % vec == 0 && x_batch_stride % vec == 0 && x_group_stride % vec == 0 && x_rank_stride % vec == 0 &&
@@ -514,6 +580,18 @@ extern "C" int xp_ss2d_dt_proj(const void* dts_r, const float* weight, void* del
     if (B == 0) return XP_OK;
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid((unsigned)ceil_div(L, 32 * vec), (unsigned)(B * G));
+    if (R > 8) {
+        const size_t smem = (size_t)D * 8 * 4;
+        if (dtype == XP_F16)
+            ss2d_dt_proj16_kernel<__half, 8><<<grid, 256, smem, st>>>((const __half*)dts_r, weight, (__half*)delta, (int)G, (int)D,
+                                                                       (int)R, L, x_batch_stride, x_group_stride, x_rank_stride);
+        else
+            ss2d_dt_proj16_kernel<__nv_bfloat16, 8><<<grid, 256, smem, st>>>((const __nv_bfloat16*)dts_r, weight,
+                                                                              (__nv_bfloat16*)delta, (int)G, (int)D, (int)R, L,
+                                                                              x_batch_stride, x_group_stride, x_rank_stride);
+        XP_LAUNCH_CHECK("ss2d_dt_proj16_kernel");
+        return XP_OK;
+    }
 #define XP_DT(T) ss2d_dt_proj_kernel<T><<<grid, 256, 0, st>>>((const T*)dts_r, weight, (T*)delta, (int)G, (int)D, (int)R, L, \
                                                                x_batch_stride, x_group_stride, x_rank_stride)
     if (dtype == XP_F32) XP_DT(float);

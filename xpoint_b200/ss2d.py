@@ -91,8 +91,10 @@ def ss2d_dt_proj(dts_r: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def dt_proj_supported(R: int, L: int, dtype: torch.dtype, batch_groups: int) -> bool:
-    return R <= 8 and L % (4 if dtype == torch.float32 else 8) == 0 and batch_groups <= 65535
+def dt_proj_supported(R: int, L: int, dtype: torch.dtype, batch_groups: int, D: int = 0) -> bool:
+    """Ranks 1..8 (any dtype) and 9..16 (16-bit inputs; FHFMA kernel) run on xp_ss2d_dt_proj."""
+    ok_rank = R <= 8 or (R <= 16 and dtype != torch.float32 and D <= 1536)
+    return ok_rank and L % (4 if dtype == torch.float32 else 8) == 0 and batch_groups <= 65535
 
 
 def fused_supported(H: int, W: int, D: int, d_state: int) -> bool:

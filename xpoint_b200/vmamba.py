@@ -259,7 +259,7 @@ class SS2D(nn.Module):
                                  reverse_group_mask=_ss2d.REVERSE_MASK, dt_weight=w["wdt_scan"])
             return _ss2d.ss2d_merge_norm(ys.view(B, K, D, L), H, W, w["norm_w"], w["norm_b"], zact, self.out_norm.eps,
                                          out_dtype=out_dtype or xx.dtype)
-        if _ss2d.dt_proj_supported(R, L, x_dbl.dtype, B * K):
+        if _ss2d.dt_proj_supported(R, L, x_dbl.dtype, B * K, D):
             dts = _ss2d.ss2d_dt_proj(x_dbl[:, :, :R], w["wdt32"])                  # (B, 4, D, L), store-bound kernel
         else:
             dts = torch.matmul(w["wdt"], x_dbl.view(B, 2, 2, R + 2 * N, L)[:, :, :, :R])   # (B, 2, 2, D, L)

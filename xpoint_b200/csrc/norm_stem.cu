@@ -146,13 +146,17 @@ __global__ void __launch_bounds__(256) add_layer_norm_scalar_kernel(const AddLnP
 // One thread = one output token, all C1 (<= 64) channels in registers; weights broadcast from shared memory.
 constexpr int STEM_MAXC = 64;
 
-template <int CIN>
+// CT: compile-time channel count (48 for XPoint: registers and loops sized exactly), 0 = runtime C1 <= STEM_MAXC
+template <int CIN, int CT>
 __global__ void __launch_bounds__(128) patch_embed_stem_kernel(const float* __restrict__ img, const float* __restrict__ wgt,
                                                                const float* __restrict__ bias, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, void* __restrict__ out, int B,
                                                                int H, int W, int C1, float eps, int out_dt, int gelu) {
     __shared__ __align__(16) float sw[CIN * 9 * STEM_MAXC];     // [cin][tap][channel], channels padded to STEM_MAXC
     __shared__ float sb[STEM_MAXC], sg[STEM_MAXC], sbe[STEM_MAXC];
+    constexpr int CC = CT ? CT : STEM_MAXC;                     // accumulators per thread
+    if (CT) C1 = CT;
+    __shared__ uint4 stage[128 * (CC / 8)];                     // 16-bit outputs leave through a per-warp transpose
     const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;               // k3 s2 p1
     for (int i = threadIdx.x; i < CIN * 9 * STEM_MAXC; i += blockDim.x) {
         const int c = i % STEM_MAXC, tap = (i / STEM_MAXC) % 9, ci = i / (STEM_MAXC * 9);
@@ -165,13 +169,14 @@ __global__ void __launch_bounds__(128) patch_embed_stem_kernel(const float* __re
     }
     __syncthreads();
     const int64_t total = (int64_t)B * Ho * Wo;
-    const int64_t tok = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tok >= total) return;
+    const int64_t tok_raw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = tok_raw < total;
+    const int64_t tok = live ? tok_raw : total - 1;             // dead threads of the last CTA redo the last token (no store)
     const int wo = (int)(tok % Wo), ho = (int)((tok / Wo) % Ho);
     const int64_t b = tok / ((int64_t)Wo * Ho);
-    float acc[STEM_MAXC];
+    float acc[CC];
 #pragma unroll
-    for (int c = 0; c < STEM_MAXC; ++c) acc[c] = sb[c];
+    for (int c = 0; c < CC; ++c) acc[c] = sb[c];
 #pragma unroll
     for (int ci = 0; ci < CIN; ++ci) {
         const float* plane = img + (b * CIN + ci) * (int64_t)H * W;
@@ -184,7 +189,7 @@ __global__ void __launch_bounds__(128) patch_embed_stem_kernel(const float* __re
                 const float px = (h >= 0 && h < H && w >= 0 && w < W) ? __ldg(plane + (int64_t)h * W + w) : 0.0f;
                 const float4* wv = reinterpret_cast<const float4*>(sw + (ci * 9 + ky * 3 + kx) * STEM_MAXC);
 #pragma unroll
-                for (int q = 0; q < STEM_MAXC / 4; ++q) {
+                for (int q = 0; q < CC / 4; ++q) {
                     if (4 * q < C1) {                      // uniform: skips the padded channel quads
                         const float4 w4 = wv[q];
                         acc[4 * q] = fmaf(px, w4.x, acc[4 * q]);
@@ -198,11 +203,11 @@ __global__ void __launch_bounds__(128) patch_embed_stem_kernel(const float* __re
     }
     float s = 0.0f;
 #pragma unroll
-    for (int c = 0; c < STEM_MAXC; ++c) s += c < C1 ? acc[c] : 0.0f;
+    for (int c = 0; c < CC; ++c) s += c < C1 ? acc[c] : 0.0f;
     const float mean = s / (float)C1;
     float ss = 0.0f;
 #pragma unroll
-    for (int c = 0; c < STEM_MAXC; ++c) {
+    for (int c = 0; c < CC; ++c) {
         const float d = c < C1 ? acc[c] - mean : 0.0f;
         acc[c] = d;
         ss = fmaf(d, d, ss);
@@ -210,7 +215,7 @@ __global__ void __launch_bounds__(128) patch_embed_stem_kernel(const float* __re
     const float rstd = rsqrtf(ss / (float)C1 + eps);
     const int64_t o = tok * C1;
 #pragma unroll
-    for (int c = 0; c < STEM_MAXC; ++c) {
+    for (int c = 0; c < CC; ++c) {
         if (c < C1) {
             float v = fmaf(acc[c] * rstd, sg[c], sbe[c]);
             if (gelu) v = gelu_erf_f(v);                                     // exact (erf) GELU, nn.GELU default
@@ -219,12 +224,17 @@ __global__ void __launch_bounds__(128) patch_embed_stem_kernel(const float* __re
     }
     if (out_dt == XP_F32) {
         float* dst = reinterpret_cast<float*>(out) + o;
+        if (live) {
 #pragma unroll
-        for (int c = 0; c < STEM_MAXC; ++c) if (c < C1) dst[c] = acc[c];
-    } else if (C1 % 8 == 0) {                               // 16-byte stores (o*2 bytes is 16-byte aligned when C1 % 8 == 0)
-        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(out) + o);
+            for (int c = 0; c < CC; ++c) if (c < C1) dst[c] = acc[c];
+        }
+    } else if (C1 % 8 == 0) {
+        // the warp's 32 tokens are one contiguous run of 32 * C1 * 2 bytes: pack to 16-byte chunks, transpose through shared
+        // memory and store whole 512-byte lines per instruction (a thread-per-token store touches 32 half-used sectors)
+        const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5, nq = C1 / 8;
+        uint4* wst = stage + wrp * 32 * (CC / 8);
 #pragma unroll
-        for (int q = 0; q < STEM_MAXC / 8; ++q) {
+        for (int q = 0; q < CC / 8; ++q) {
             if (8 * q < C1) {
                 uint4 raw;
                 if (out_dt == XP_F16) {
@@ -236,12 +246,17 @@ __global__ void __launch_bounds__(128) patch_embed_stem_kernel(const float* __re
 #pragma unroll
                     for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(acc[8 * q + 2 * j], acc[8 * q + 2 * j + 1]);
                 }
-                dst[q] = raw;
+                wst[lane * nq + q] = raw;
             }
         }
-    } else {
+        __syncwarp();
+        const int64_t tok0 = (int64_t)blockIdx.x * blockDim.x + wrp * 32;           // first token of the warp
+        const int64_t nvalid = min((int64_t)32, total - tok0);                    // <= 0 for fully dead warps
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(out) + tok0 * C1);
+        for (int i = lane; i < nvalid * nq; i += 32) dst[i] = wst[i];
+    } else if (live) {
 #pragma unroll
-        for (int c = 0; c < STEM_MAXC; ++c) if (c < C1) st_from_f32(out, out_dt, o + c, acc[c]);
+        for (int c = 0; c < CC; ++c) if (c < C1) st_from_f32(out, out_dt, o + c, acc[c]);
     }
 }
 
@@ -299,12 +314,11 @@ extern "C" int xp_patch_embed_stem(const float* img, const float* weight, const 
     const int64_t total = B * ((H + 1) / 2) * ((W + 1) / 2);
     const unsigned grid = (unsigned)ceil_div(total, 128);
     cudaStream_t st = (cudaStream_t)stream;
-    if (Cin == 1)
-        patch_embed_stem_kernel<1><<<grid, 128, 0, st>>>(img, weight, bias, gamma, beta, out, (int)B, (int)H, (int)W, (int)C1, eps,
-                                                          out_dtype, gelu);
-    else
-        patch_embed_stem_kernel<3><<<grid, 128, 0, st>>>(img, weight, bias, gamma, beta, out, (int)B, (int)H, (int)W, (int)C1, eps,
-                                                          out_dtype, gelu);
+#define XP_STEM(CIN_, CT_) patch_embed_stem_kernel<CIN_, CT_><<<grid, 128, 0, st>>>(img, weight, bias, gamma, beta, out, (int)B, (int)H, \
+                                                                               (int)W, (int)C1, eps, out_dtype, gelu)
+    if (Cin == 1) { if (C1 == 48) XP_STEM(1, 48); else XP_STEM(1, 0); }
+    else { if (C1 == 48) XP_STEM(3, 48); else XP_STEM(3, 0); }
+#undef XP_STEM
     XP_LAUNCH_CHECK("patch_embed_stem_kernel");
     return XP_OK;
 }

@@ -358,10 +358,11 @@ __global__ void __launch_bounds__(256) ss2d_dt_proj_kernel(const T* __restrict__
                                                            int G, int D, int R, int64_t L, int64_t x_bs, int64_t x_gs,
                                                            int64_t x_rs) {
     constexpr int VEC = 16 / (int)sizeof(T);          // tokens per thread (8 for 16-bit, 4 for fp32)
-    const int tg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    // the 8 warps of a CTA cover ADJACENT token ranges and walk the channel rows together: at any moment the CTA writes
+    // one 4 KiB (2 KiB for fp32 ... 16-byte x 256 threads) run of a delta row, which DRAM takes far better than 8 rows apart
     const int64_t bg = blockIdx.y;
     const int64_t b = bg / G, g = bg % G;
-    const int64_t l0 = ((int64_t)blockIdx.x * 32 + tg) * VEC;
+    const int64_t l0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * VEC;
     if (l0 >= L) return;                               // L % VEC == 0: token groups are all-or-nothing
     float x[8][VEC];
     const T* src = xr + b * x_bs + g * x_gs + l0;
@@ -376,7 +377,7 @@ __global__ void __launch_bounds__(256) ss2d_dt_proj_kernel(const T* __restrict__
     }
     const float* Wg = Wt + g * (int64_t)D * R;
     T* dst = out + (bg * D) * L + l0;
-    for (int d = rl; d < D; d += 8) {
+    for (int d = 0; d < D; ++d) {
         float acc[VEC];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) acc[j] = 0.0f;
@@ -417,7 +418,6 @@ __global__ void __launch_bounds__(256) ss2d_dt_proj16_kernel(const T* __restrict
                                                              T* __restrict__ out, int G, int D, int R, int64_t L, int64_t x_bs,
                                                              int64_t x_gs, int64_t x_rs) {
     extern __shared__ uint32_t wsm[];                  // [D][RP] weight pairs (W[d][2q], W[d][2q+1]) in T, zero-padded
-    const int tg = threadIdx.x & 31, rl = threadIdx.x >> 5;
     const int64_t bg = blockIdx.y;
     const int64_t b = bg / G, g = bg % G;
     const float* Wg = Wt + g * (int64_t)D * R;
@@ -429,14 +429,14 @@ __global__ void __launch_bounds__(256) ss2d_dt_proj16_kernel(const T* __restrict
                  ((uint32_t)*reinterpret_cast<const unsigned short*>(&hi) << 16);
     }
     __syncthreads();
-    const int64_t l0 = ((int64_t)blockIdx.x * 32 + tg) * 8;
+    const int64_t l0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 8;    // warps side by side along the tokens (see above)
     if (l0 >= L) return;                               // L % 8 == 0: token groups are all-or-nothing
     uint4 x[2 * RP];
     const T* src = xr + b * x_bs + g * x_gs + l0;
 #pragma unroll
     for (int r = 0; r < 2 * RP; ++r) x[r] = r < R ? __ldg(reinterpret_cast<const uint4*>(src + r * x_rs)) : make_uint4(0u, 0u, 0u, 0u);
     T* dst = out + (bg * D) * L + l0;
-    for (int d = rl; d < D; d += 8) {
+    for (int d = 0; d < D; ++d) {
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
@@ -579,7 +579,7 @@ extern "C" int xp_ss2d_dt_proj(const void* dts_r, const float* weight, void* del
     XP_REQUIRE(B * G <= 65535, "xp_ss2d_dt_proj: batch * groups must be <= 65535");
     if (B == 0) return XP_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid((unsigned)ceil_div(L, 32 * vec), (unsigned)(B * G));
+    dim3 grid((unsigned)ceil_div(L, 256 * vec), (unsigned)(B * G));
     if (R > 8) {
         const size_t smem = (size_t)D * 8 * 4;
         if (dtype == XP_F16)

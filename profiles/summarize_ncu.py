@@ -22,7 +22,10 @@ KEYS = [
     ("lts__t_sector_hit_rate.pct", "L2 hit rate %"),
 ]
 for rep in sys.argv[1:]:
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):     # `ncu -i x.ncu-rep --page raw --csv` exported on the GPU box
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     if len(rows) < 3:
         print(f"## {rep}: no data"); continue

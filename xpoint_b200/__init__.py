@@ -13,6 +13,6 @@ from .postprocess import (DMatch, NNMatcher, box_nms, detector_post, get_matches
                           nms_keypoints, normalize_descriptors, sample_descriptors)
 from .selective_scan import (SelectiveScanCuda, selective_scan_cuda_oflex, selective_scan_fn, selective_scan_fn_mamba)
 from .vmamba import PRESETS, SS2D, VSSM, VSSBlock, build_vssm
-from .xpoint import PairPipeline, PairResult, XPoint
+from .xpoint import GraphedPairPipeline, PairPipeline, PairResult, XPoint
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -298,9 +298,49 @@ class PairPipeline:
         return PairResult(kps.keypoints[:B], kps.keypoints[B:], count[:B], count[B:], d[:B], d[B:], m.match_idx,
                           m.match_dist, m.count)
 
+    def capture(self, optical: torch.Tensor, thermal: torch.Tensor, warmup: int = 3) -> "GraphedPairPipeline":
+        """Record one whole step (encoder, heads, NMS, sampling, matching: ~180 launches of this library, cuBLAS and cuDNN)
+        into a CUDA graph for the shapes of ``optical`` / ``thermal``.  The step has no host synchronisation and no
+        data-dependent launch shape, so a replay is the same work without the per-launch host cost and the gaps it leaves
+        on the device."""
+        return GraphedPairPipeline(self, optical, thermal, warmup)
+
     @torch.no_grad()
     def __call__(self, optical: torch.Tensor, thermal: torch.Tensor) -> PairResult:
         out = self.net.forward_pair_batched(optical, thermal, want_desc=False, split=False)
         if out.get("desc_cl") is not None:
             return self.tail_batched(out["prob"], out["desc_cl"], channel_last=True)
         return self.tail_batched(out["prob"], out["desc"])
+
+
+class GraphedPairPipeline:
+    """A PairPipeline step replayed from a CUDA graph.  ``__call__(optical, thermal)`` copies the images into the graph's
+    static input buffers (device-to-device, or host-to-device for pinned host tensors), replays, and returns the PairResult
+    whose tensors are the graph's static outputs -- valid until the next call."""
+
+    def __init__(self, pipe: PairPipeline, optical: torch.Tensor, thermal: torch.Tensor, warmup: int = 3):
+        if not optical.is_cuda:
+            raise RuntimeError("GraphedPairPipeline.capture needs CUDA example inputs (their shapes are baked into the graph)")
+        self.pipe = pipe
+        self.static_o, self.static_t = optical.clone(), thermal.clone()
+        side = torch.cuda.Stream(device=optical.device)
+        side.wait_stream(torch.cuda.current_stream(optical.device))
+        with torch.cuda.stream(side):           # warm-up on a side stream: lazy initialisation must not be captured
+            for _ in range(max(warmup, 1)):
+                pipe(self.static_o, self.static_t)
+        torch.cuda.current_stream(optical.device).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.result = pipe(self.static_o, self.static_t)
+
+    def load(self, optical: torch.Tensor, thermal: torch.Tensor, non_blocking: bool = True) -> None:
+        self.static_o.copy_(optical, non_blocking=non_blocking)
+        self.static_t.copy_(thermal, non_blocking=non_blocking)
+
+    def replay(self) -> PairResult:
+        self.graph.replay()
+        return self.result
+
+    def __call__(self, optical: torch.Tensor, thermal: torch.Tensor) -> PairResult:
+        self.load(optical, thermal)
+        return self.replay()

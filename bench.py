@@ -364,14 +364,14 @@ def run_ours(args):
     dom = by_shape[dom_key]
     dom_bytes, dom_ms = dom[2] / dom[0], dom[1] / dom[0]
     dom_gbs = dom_bytes / dom_ms / 1e6
-    # DRAM bytes of ONE launch of that shape from `ncu --set full` (profiles/r1_s2_summary.md): only known for the
+    # DRAM bytes of ONE launch of that shape from `ncu --set full` (profiles/r1_s3_summary.md): only known for the
     # default workload (preset E, fp16 autocast, 64 pairs of 512x640 -> B128 KD384 K4 N1 L20480 float16->float32)
-    ncu_traffic = {"B128 KD384 K4 N1 L20480 float16->float32": 4.074573e9 + 3.980505e9}
+    ncu_traffic = {"B128 KD384 K4 N1 L20480 float16->float32": 4.075503e9 + 3.980529e9}
     roofline = {"bound": "hbm", "kernel": f"xp_selective_scan_fwd -> scan_lanes_kernel, launch shape {dom_key}",
                 "achieved": round(dom_gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(dom_gbs / peak, 4),
                 "traffic": ncu_traffic.get(dom_key), "algorithmic_bytes_per_launch": int(dom_bytes),
                 "ms_per_launch": round(dom_ms, 4), "peak_source": peak_src,
-                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_s2_summary.md",
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_s3_summary.md",
                 "launches": dom[0], "share_of_step": round(dom[1] / ms_eager, 4),
                 "measured_in": "eager pass of the same K steps inside this process (CUDA events around each launch); the timed "
                                "region replays the same kernels from a CUDA graph" if graphed is not None else "timed region",

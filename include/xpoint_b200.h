@@ -290,6 +290,22 @@ XP_API int xp_mnn_match(const float* d1, const float* d2, const int32_t* n1, con
                  float* match_dist, int32_t* match_count, int32_t use_tensor_cores, void* workspace,
                  int64_t workspace_bytes, xp_stream_t stream);
 
+/* -- f3 ("next" row): homography from the mutual matches -----------------------------------------
+ * Replaces the per-pair CPU call cv2.findHomography(optical_pts, thermal_pts, USAC_MAGSAC, ransacReprojThreshold,
+ * confidence 0.9999, maxIters 10000) of the evaluation (xpoint/utils/evaluation.py:359-378; points are (x, y) =
+ * (kp[1], kp[0]), H maps image-1 points onto image-2 points) for the whole batch, without leaving the GPU.
+ * OpenCV's USAC is randomised and version-dependent, so the contract is H and the inlier set, not its internals: this is a
+ * deterministic LO-RANSAC (hash-sampled 4-point DLT hypotheses, forward transfer error < reproj_threshold, most inliers /
+ * lowest index wins, lo_rounds least-squares refits over the inliers), fp64, restated line by line in the oracle.
+ *   kp1, kp2 (B, k, 2) int32 (y, x); n1 (B) int32 valid rows of kp1 (NULL = k); match_idx (B, k) int32: row of kp2 matched
+ *   to kp1 row i, or -1.  H (B, 3, 3) fp64 row-major with H[2][2] = 1; inlier_mask (B, k) u8 per kp1 row (nullable);
+ *   n_inliers (B) int32, -1 when fewer than 4 matches / no valid hypothesis (the reference's H_est = None; H is 0 then).
+ */
+XP_API int xp_estimate_homography(const int32_t* kp1, const int32_t* kp2, const int32_t* n1, const int32_t* match_idx,
+                                  int64_t B, int64_t k, int64_t height, int64_t width, int32_t iters, float reproj_threshold,
+                                  int32_t lo_rounds, uint32_t seed, double* H, uint8_t* inlier_mask, int32_t* n_inliers,
+                                  xp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -286,7 +286,48 @@ def gen_model():
         print(tag, "params", sum(p.numel() for p in net.parameters()))
 
 
+def gen_homography():
+    """The reference's homography step, exactly as evaluation.py:359-378 calls it: cv2.findHomography(optical_pts, thermal_pts,
+    USAC_MAGSAC, ransacReprojThreshold=3, confidence=0.9999, maxIters=10000) on (x, y) float32 points shaped (-1, 1, 2).
+    Synthetic matches: integer keypoints of a 512x640 pair related by a known homography (+ rounding noise) and a share of
+    wrong matches; the fixture keeps the keypoints, the match list, the ground truth, OpenCV's H and its inlier mask."""
+    import cv2
+    rng = np.random.default_rng(0)
+    Hh, Ww, k = 512, 640, 1500
+    cases = {}
+    for name, outlier_share, n_match in (("easy", 0.1, 1200), ("hard", 0.6, 900), ("few", 0.3, 12)):
+        ang, sc = rng.uniform(-0.2, 0.2), rng.uniform(0.9, 1.1)
+        Hgt = np.array([[sc * np.cos(ang), -sc * np.sin(ang), rng.uniform(-30, 30)],
+                        [sc * np.sin(ang), sc * np.cos(ang), rng.uniform(-30, 30)],
+                        [rng.uniform(-1e-4, 1e-4), rng.uniform(-1e-4, 1e-4), 1.0]])
+        kp1 = np.stack([rng.integers(0, Hh, k), rng.integers(0, Ww, k)], 1).astype(np.int32)       # (y, x)
+        xy1 = np.concatenate([kp1[:, ::-1].astype(np.float64), np.ones((k, 1))], 1)
+        w = xy1 @ Hgt.T
+        xy2 = w[:, :2] / w[:, 2:]
+        kp2 = np.round(xy2[:, ::-1]).astype(np.int32)                                             # (y, x), rounded to pixels
+        perm = rng.permutation(k)
+        kp2s = kp2[perm]                                    # image-2 keypoints in their own order
+        inv = np.argsort(perm)                              # kp1 row i <-> kp2s row inv[i]
+        match_idx = np.full(k, -1, np.int32)
+        rows = rng.choice(k, n_match, replace=False)
+        match_idx[rows] = inv[rows]
+        wrong = rows[rng.random(n_match) < outlier_share]
+        match_idx[wrong] = rng.integers(0, k, wrong.size)
+        inb = (kp2s[:, 0] >= 0) & (kp2s[:, 0] < Hh) & (kp2s[:, 1] >= 0) & (kp2s[:, 1] < Ww)
+        match_idx[(match_idx >= 0) & ~inb[np.maximum(match_idx, 0)]] = -1
+        q = np.nonzero(match_idx >= 0)[0]
+        optical_pts = np.float32(kp1[q][:, ::-1]).reshape(-1, 1, 2)
+        thermal_pts = np.float32(kp2s[match_idx[q]][:, ::-1]).reshape(-1, 1, 2)
+        cv2.setRNGSeed(0)
+        H_cv, mask = cv2.findHomography(optical_pts, thermal_pts, method=cv2.USAC_MAGSAC, ransacReprojThreshold=3.0,
+                                        confidence=0.9999, maxIters=10000)
+        cases.update({f"{name}_kp1": kp1, f"{name}_kp2": kp2s, f"{name}_match_idx": match_idx, f"{name}_H_gt": Hgt,
+                      f"{name}_H_cv": H_cv, f"{name}_mask_cv": mask.ravel().astype(np.uint8), f"{name}_query": q.astype(np.int32)})
+        print(name, "matches", q.size, "cv2 inliers", int(mask.sum()))
+    save("homography", height=np.int32(Hh), width=np.int32(Ww), cv2_version=np.array(cv2.__version__), **cases)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["scan", "cross", "ss2d", "tail", "match", "model"]
+    which = sys.argv[1:] or ["scan", "cross", "ss2d", "tail", "match", "model", "homography"]
     for w in which:
         globals()["gen_" + w]()

@@ -262,3 +262,93 @@ def test_match_config5_size_16384():
     nn21 = r_tc.nn21[0].cpu().numpy()
     q = np.nonzero(m_tc >= 0)[0]
     assert np.array_equal(nn21[m_tc[q]], q)
+
+
+def _hom_inputs(seed, B, k, Hh, Ww, outliers):
+    rng = np.random.default_rng(seed)
+    kp1 = np.stack([rng.integers(0, Hh, (B, k)), rng.integers(0, Ww, (B, k))], -1).astype(np.int32)
+    kp2 = np.zeros_like(kp1)
+    mi = np.full((B, k), -1, np.int32)
+    n1 = np.zeros(B, np.int32)
+    for b in range(B):
+        ang, sc = rng.uniform(-0.3, 0.3), rng.uniform(0.8, 1.2)
+        Hgt = np.array([[sc * np.cos(ang), -sc * np.sin(ang), rng.uniform(-40, 40)],
+                        [sc * np.sin(ang), sc * np.cos(ang), rng.uniform(-40, 40)], [rng.uniform(-2e-4, 2e-4), 0.0, 1.0]])
+        xy = np.concatenate([kp1[b][:, ::-1].astype(float), np.ones((k, 1))], 1) @ Hgt.T
+        kp2b = np.round((xy[:, :2] / xy[:, 2:])[:, ::-1]).astype(np.int32)
+        perm = rng.permutation(k)
+        kp2[b] = kp2b[perm]
+        inv = np.argsort(perm)
+        n1[b] = rng.integers(k // 2, k + 1)
+        rows = rng.choice(k, int(0.7 * k), replace=False)
+        mi[b, rows] = inv[rows]
+        wrong = rows[rng.random(rows.size) < outliers]
+        mi[b, wrong] = rng.integers(0, k, wrong.size)
+    return kp1, kp2, mi, n1
+
+
+@pytest.mark.parametrize("B,k,outliers", [(3, 1024, 0.3), (2, 4096, 0.6), (4, 200, 0.1)])
+def test_homography_vs_oracle(B, k, outliers):
+    """xp_estimate_homography against its oracle restatement: same winning inlier set (the fp64 arithmetic of hypothesis
+    scoring is identical on both sides), H to 1e-8 (the least-squares sums are added in a different order)."""
+    X, O = _imports()
+    Hh, Ww = 512, 640
+    kp1, kp2, mi, n1 = _hom_inputs(k + B, B, k, Hh, Ww, outliers)
+    r = X.estimate_homography(torch.from_numpy(kp1).to(DEV), torch.from_numpy(kp2).to(DEV), torch.from_numpy(mi).to(DEV), Hh, Ww,
+                              n1=torch.from_numpy(n1).to(DEV))
+    assert r.H.dtype == torch.float64 and r.H.shape == (B, 3, 3) and r.inliers.shape == (B, k)
+    for b in range(B):
+        H, inl, cnt, _ = O.estimate_homography(kp1[b], kp2[b], mi[b], Hh, Ww, n1=int(n1[b]), pair_index=b)
+        assert int(r.n_inliers[b]) == cnt
+        assert np.array_equal(r.inliers[b].cpu().numpy(), inl)
+        np.testing.assert_allclose(r.H[b].cpu().numpy(), H, rtol=1e-8, atol=1e-8)
+        assert cnt >= 0.5 * (1 - outliers) * (mi[b, : n1[b]] >= 0).sum()
+
+
+def test_homography_golden_and_degenerate():
+    """The OpenCV fixtures (tests/golden/homography.npz) through the GPU path, the cv2-shaped wrapper, and pairs without
+    an estimate."""
+    X, O = _imports()
+    g = golden("homography")
+    Hh, Ww = int(g["height"]), int(g["width"])
+    for name in ("easy", "hard", "few"):
+        kp1, kp2, mi, q = (torch.from_numpy(g[name + k]).to(DEV) for k in ("_kp1", "_kp2", "_match_idx", "_query"))
+        r = X.estimate_homography(kp1[None], kp2[None], mi[None], Hh, Ww)
+        mask_cv = g[name + "_mask_cv"].astype(bool)
+        assert (r.inliers[0][q.long()].cpu().numpy() == mask_cv).mean() >= 0.98
+        c = np.array([[0, 0, 1], [Ww, 0, 1], [0, Hh, 1], [Ww, Hh, 1]], float)
+        a, bb = c @ r.H[0].cpu().numpy().T, c @ g[name + "_H_gt"].T
+        assert np.linalg.norm(a[:, :2] / a[:, 2:] - bb[:, :2] / bb[:, 2:], axis=1).mean() < 2.0
+        # the call shape of evaluation.py:368-375
+        src = kp1[q.long()].flip(-1).float().reshape(-1, 1, 2)
+        dst = kp2[mi[q.long()].long()].flip(-1).float().reshape(-1, 1, 2)
+        H2, m2 = X.find_homography(src, dst, 3.0, Hh, Ww)
+        assert H2 is not None and m2.shape == (len(q), 1) and (m2[:, 0].bool().cpu().numpy() == mask_cv).mean() >= 0.98
+    kp1 = torch.from_numpy(g["easy_kp1"]).to(DEV)[None]
+    kp2 = torch.from_numpy(g["easy_kp2"]).to(DEV)[None]
+    mi = torch.full((1, kp1.shape[1]), -1, dtype=torch.int32, device=DEV)
+    mi[0, :3] = torch.tensor([5, 6, 7], dtype=torch.int32)
+    r = X.estimate_homography(kp1, kp2, mi, Hh, Ww)
+    assert int(r.n_inliers[0]) == -1 and float(r.H.abs().sum()) == 0.0 and not bool(r.inliers.any())
+    assert X.find_homography(torch.zeros(3, 2, device=DEV), torch.zeros(3, 2, device=DEV))[0] is None
+    with pytest.raises(RuntimeError):
+        X.estimate_homography(kp1, kp2, mi[:, :5], Hh, Ww)
+
+
+def test_pipeline_with_homography():
+    """PairPipeline(estimate_homography=True): thermal map = optical map shifted by (7, -5) pixels -> H is that translation."""
+    X, O = _imports()
+    g = torch.Generator().manual_seed(3)
+    B, H, W, k = 2, 256, 320, 512
+    prob_o = torch.rand(B, 1, H, W, generator=g) ** 6
+    prob_t = torch.roll(prob_o, shifts=(7, -5), dims=(2, 3))
+    desc_o = torch.nn.functional.normalize(torch.randn(B, 256, H // 8, W // 8, generator=g), dim=1)
+    pipe = X.PairPipeline(None, nms=8, detection_threshold=0.015, keep_top_k=k, estimate_homography=True)
+    # descriptors: sample the same field for both (a match is then decided by position only for identical maps)
+    r = pipe.tail(prob_o.to(DEV), prob_o.to(DEV), desc_o.to(DEV), desc_o.to(DEV))
+    assert r.H.shape == (B, 3, 3) and r.inliers.shape == (B, k)
+    eye = torch.eye(3, dtype=torch.float64, device=DEV)
+    for b in range(B):
+        assert int(r.n_inliers[b]) == int(r.n_matches[b]) == k          # identical images: every keypoint matches itself
+        assert torch.allclose(r.H[b], eye, atol=1e-9)
+    del prob_t

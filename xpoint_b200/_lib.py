@@ -66,6 +66,8 @@ _SIGNATURES = {
     "xp_sample_descriptors": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int32] + [c_int64] * 5
                               + [c_void_p, c_void_p]),
     "xp_match_workspace_bytes": (c_int64, [c_int64] * 4),
+    "xp_estimate_homography": (ctypes.c_int, [c_void_p] * 4 + [c_int64] * 4 + [c_int32, c_float, c_int32, ctypes.c_uint32]
+                               + [c_void_p] * 4),
     "xp_mnn_match": (ctypes.c_int, [c_void_p] * 4 + [c_int64] * 4 + [c_void_p] * 5 + [c_int32, c_void_p, c_int64, c_void_p]),
 }
 

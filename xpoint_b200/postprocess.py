@@ -290,3 +290,61 @@ def get_matches(desc_1, desc_2, method="bfmatcher", knn_matches=False, **kwargs)
     if method in ("flann", "thresholdmatcher"):
         raise NotImplementedError(f"method {method!r} is outside the accelerated hot path")
     raise ValueError("unknown matching method")
+
+
+# ------------------------------------------------------------------------------------------ homography
+class Homographies(NamedTuple):
+    H: torch.Tensor            # (B, 3, 3) float64, maps image-1 (x, y) onto image-2; zeros where n_inliers == -1
+    inliers: torch.Tensor      # (B, k) bool per keypoint row of image 1
+    n_inliers: torch.Tensor    # (B,) int32, -1 = no estimate (fewer than 4 matches: the reference's H_est = None)
+
+
+def estimate_homography(kp1: torch.Tensor, kp2: torch.Tensor, match_idx: torch.Tensor, height: int, width: int,
+                        n1: Optional[torch.Tensor] = None, iters: int = 2048, reproj_threshold: float = 3.0,
+                        lo_rounds: int = 2, seed: int = 0) -> Homographies:
+    """Batched replacement of the per-pair ``cv2.findHomography(optical_pts, thermal_pts, USAC_MAGSAC, thr, ...)`` of the
+    evaluation (xpoint/utils/evaluation.py:359-378) on the GPU: kp1, kp2 (B, k, 2) int32 (y, x), match_idx (B, k) int32
+    (row of kp2 matched to kp1 row i, -1 = none), n1 (B,) valid rows of kp1.  Deterministic LO-RANSAC, no host sync."""
+    dev = _lib.require_cuda(kp1, kp2, match_idx, n1)
+    if kp1.dim() != 3 or kp1.shape[2] != 2 or kp2.dim() != 3 or kp2.shape[0] != kp1.shape[0] or kp2.shape[2] != 2:
+        raise RuntimeError("estimate_homography: kp1 / kp2 must be (B, k, 2) keypoint tensors")
+    B, k, _ = kp1.shape
+    if tuple(match_idx.shape) != (B, k):
+        raise RuntimeError("estimate_homography: match_idx must be (B, k)")
+    kp1 = kp1.to(torch.int32).contiguous()
+    kp2 = kp2.to(torch.int32).contiguous()
+    match_idx = match_idx.to(torch.int32).contiguous()
+    n1 = None if n1 is None else n1.to(torch.int32).contiguous()
+    H = torch.empty((B, 3, 3), dtype=torch.float64, device=dev)
+    inl = torch.empty((B, k), dtype=torch.uint8, device=dev)
+    cnt = torch.empty((B,), dtype=torch.int32, device=dev)
+    if B:
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().xp_estimate_homography(_lib.ptr(kp1), _lib.ptr(kp2), _lib.ptr(n1), _lib.ptr(match_idx), B, k,
+                                                         int(height), int(width), int(iters), float(reproj_threshold),
+                                                         int(lo_rounds), int(seed) & 0xffffffff, _lib.ptr(H), _lib.ptr(inl),
+                                                         _lib.ptr(cnt), _lib.stream_ptr(dev)))
+        _lib.count_launches(1)
+    return Homographies(H, inl.bool(), cnt)
+
+
+def find_homography(src_pts, dst_pts, reproj_threshold: float = 3.0, height: Optional[int] = None, width: Optional[int] = None,
+                    iters: int = 2048, seed: int = 0):
+    """cv2.findHomography-shaped convenience for one pair (evaluation.py:368-375): src_pts, dst_pts (N, 2) or (N, 1, 2)
+    CUDA tensors of (x, y) pixel coordinates (integers, as keypoints are) -> (H (3, 3) float64 or None, mask (N, 1) uint8)."""
+    s = src_pts.reshape(-1, 2)
+    d = dst_pts.reshape(-1, 2)
+    n = s.shape[0]
+    if n < 4:
+        return None, torch.zeros((n, 1), dtype=torch.uint8, device=s.device)
+    if height is None:
+        height = int(max(float(s[:, 1].max()), float(d[:, 1].max()))) + 1
+    if width is None:
+        width = int(max(float(s[:, 0].max()), float(d[:, 0].max()))) + 1
+    kp1 = s.flip(-1).round().to(torch.int32)[None]
+    kp2 = d.flip(-1).round().to(torch.int32)[None]
+    idx = torch.arange(n, dtype=torch.int32, device=s.device)[None]
+    r = estimate_homography(kp1, kp2, idx, height, width, None, iters, reproj_threshold, 2, seed)
+    if int(r.n_inliers[0]) < 0:
+        return None, torch.zeros((n, 1), dtype=torch.uint8, device=s.device)
+    return r.H[0], r.inliers[0].to(torch.uint8)[:, None]

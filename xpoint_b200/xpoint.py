@@ -269,6 +269,9 @@ class PairResult(NamedTuple):
     match_idx: torch.Tensor       # (B, k) int32, thermal keypoint index matched to optical keypoint i, or -1
     match_dist: torch.Tensor      # (B, k) fp32
     n_matches: torch.Tensor       # (B,) int32
+    H: Optional[torch.Tensor] = None           # (B, 3, 3) float64 optical -> thermal, with estimate_homography=True
+    inliers: Optional[torch.Tensor] = None     # (B, k) bool per optical keypoint
+    n_inliers: Optional[torch.Tensor] = None   # (B,) int32, -1 = no estimate
 
 
 class PairPipeline:
@@ -276,10 +279,13 @@ class PairPipeline:
     (xpoint/utils/evaluation.py:229-301 with configs/cipdp.yaml:52-55: nms 8, detection_threshold 0.015)."""
 
     def __init__(self, net: Optional[XPoint], nms=8, detection_threshold=0.015, iou=0.1, keep_top_k=4096,
-                 use_tensor_cores=True):
+                 use_tensor_cores=True, estimate_homography=False, reprojection_threshold=3.0, ransac_iters=2048):
         self.net = net
         self.nms, self.thr, self.iou, self.topk = nms, detection_threshold, iou, keep_top_k
         self.use_tensor_cores = use_tensor_cores
+        # SURVEY 8f row f3: the step after matching in the evaluation (evaluation.py:359-378), off by default because
+        # BASELINE's step ends at the matches
+        self.estimate_homography, self.reproj_thr, self.ransac_iters = estimate_homography, reprojection_threshold, ransac_iters
 
     def tail(self, prob_o, prob_t, desc_o, desc_t, channel_last=False) -> PairResult:
         """prob (B,1,H,W) fp32; desc (B,256,Hc,Wc) fp32 [or (B,Hc,Wc,256) with channel_last] -> keypoints, descriptors
@@ -295,8 +301,12 @@ class PairPipeline:
         count = torch.clamp(kps.count, max=self.topk)
         d = pp.sample_descriptors(kps.keypoints, count, desc, H, W, channel_last)
         m = pp.mnn_match(d[:B], d[B:], count[:B], count[B:], use_tensor_cores=self.use_tensor_cores)
+        hom = (None, None, None)
+        if self.estimate_homography:
+            hom = pp.estimate_homography(kps.keypoints[:B], kps.keypoints[B:], m.match_idx, H, W, count[:B],
+                                         iters=self.ransac_iters, reproj_threshold=self.reproj_thr)
         return PairResult(kps.keypoints[:B], kps.keypoints[B:], count[:B], count[B:], d[:B], d[B:], m.match_idx,
-                          m.match_dist, m.count)
+                          m.match_dist, m.count, *hom)
 
     def capture(self, optical: torch.Tensor, thermal: torch.Tensor, warmup: int = 3) -> "GraphedPairPipeline":
         """Record one whole step (encoder, heads, NMS, sampling, matching: ~180 launches of this library, cuBLAS and cuDNN)

@@ -222,7 +222,7 @@ def mnn_match(d1: torch.Tensor, d2: torch.Tensor, n1: Optional[torch.Tensor] = N
             _lib.check(lib.xp_mnn_match(_lib.ptr(d1), _lib.ptr(d2), _lib.ptr(n1), _lib.ptr(n2), P, s1, s2, C,
                                         _lib.ptr(nn12), _lib.ptr(nn21), _lib.ptr(midx), _lib.ptr(mdist), _lib.ptr(cnt),
                                         int(bool(use_tensor_cores)), _lib.ptr(ws), nbytes, _lib.stream_ptr(dev)))
-        _lib.count_launches(5)   # 2 row-norm + 2 arg-min (or 1 fused + 1 decode) + mutual check
+        _lib.count_launches(5)   # lower bound: 2 row-norm + arg-min kernels + mutual check (the tensor-core path adds the operand splits)
     return Matches(midx, mdist, cnt, nn12, nn21)
 
 

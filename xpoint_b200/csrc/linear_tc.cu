@@ -11,9 +11,9 @@
 //   warp 1     MMA issuer (one lane): 4 x tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) per k-block into one
 //              of two TMEM accumulators; tcgen05.commit frees the stage / publishes the accumulator
 //   warp 2     TMEM allocation (512 columns)
-//   warps 4-15 epilogue: warp e owns TMEM lane quarter e % 4 and every third 32-column chunk (e / 4): tcgen05.ld,
-//              + bias (shared memory), GELU, pack to 16 bit; the 32 x 32 chunk is transposed through a padded per-warp
-//              shared-memory buffer so that every store instruction writes whole 64-byte runs (8 rows x 2 sectors).
+//   warps 4-15 epilogue: warp e owns TMEM lane quarter e % 4 and every third 64-column chunk (e / 4): tcgen05.ld,
+//              + bias (shared memory), GELU, pack to 16 bit; a 32 x 64 chunk is transposed through a padded per-warp
+//              shared-memory buffer so that every store instruction writes whole 128-byte lines (4 rows x 128 B).
 // GELU uses erf(x) = 1 - (1 + a1 x + .. + a6 x^6)^-16 (Abramowitz-Stegun 7.1.28, |err| <= 3e-7, far below the 16-bit
 // output quantum) evaluated on packed fp32 pairs instead of libdevice erff: the epilogue keeps up with the store stream.
 #include "common.cuh"
@@ -21,15 +21,15 @@
 
 namespace xp {
 
-constexpr int LT_BM = 128, LT_BK = 64, LT_STAGES = 4;
+constexpr int LT_BM = 128, LT_BK = 64;
 constexpr int LT_A_TILE = LT_BM * 128;
 constexpr int LT_EPI_WARPS = 12, LT_EPI_PARTS = LT_EPI_WARPS / 4, LT_THREADS = (4 + LT_EPI_WARPS) * 32;
-constexpr int LT_STG_PITCH = 80, LT_STG = 32 * LT_STG_PITCH;   // per-warp transpose buffer: 32 rows x (64 B + 16 B pad)
+constexpr int LT_STG_PITCH = 144, LT_STG = 32 * LT_STG_PITCH;  // per-warp transpose buffer: 32 rows x (128 B + 16 B pad)
 
-template <int BN> struct LtCfg {
+template <int BN, int LT_STAGES> struct LtCfg {
     static constexpr int W_TILE = BN * 128;
     static constexpr int STAGE = LT_A_TILE + W_TILE;
-    static constexpr int SMEM_FIXED = LT_STAGES * STAGE + 1024 /*align*/ + 256 /*barriers + tmem ptr*/ + LT_EPI_WARPS * LT_STG;
+    static constexpr int SMEM = LT_STAGES * STAGE + 1024 /*align*/ + 256 /*barriers + tmem ptr*/ + LT_EPI_WARPS * (LT_STG + 256 /*bias of the chunk*/);
 };
 
 // exact-GELU of two accumulators at once.  erf(x) = 1 - (1 + a1 x + .. + a6 x^6)^-16 for x >= 0 (Abramowitz-Stegun
@@ -54,11 +54,11 @@ __device__ __forceinline__ float2 gelu_erf2(float2 v) {
     return fma2(v, h, t);
 }
 
-template <int BN, bool GELU, bool BF16>
+template <int BN, bool GELU, bool BF16, int LT_STAGES>
 __global__ void __launch_bounds__(LT_THREADS, 1)
 linear_act_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                      const float* __restrict__ bias, void* __restrict__ out, int M, int N, int K) {
-    using Cfg = LtCfg<BN>;
+    using Cfg = LtCfg<BN, LT_STAGES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + LT_STAGES * Cfg::STAGE);
@@ -68,7 +68,7 @@ linear_act_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     uint64_t* tempty = bars + 2 * LT_STAGES + 2;   // [2]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * LT_STAGES + 4);
     uint8_t* stg_all = base + LT_STAGES * Cfg::STAGE + 256;                          // [LT_EPI_WARPS][LT_STG]
-    float* bias_s = reinterpret_cast<float*>(stg_all + LT_EPI_WARPS * LT_STG);      // [N]
+    float* bias_all = reinterpret_cast<float*>(stg_all + LT_EPI_WARPS * LT_STG);    // [LT_EPI_WARPS][64]: bias of the warp's current chunk
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = (N + BN - 1) / BN;
@@ -77,7 +77,6 @@ linear_act_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     const int my_mb = ((int)blockIdx.x < n_mb) ? (n_mb - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;   // row blocks of this CTA
     const int ntl = my_mb * n_tiles;                   // output tiles of this CTA: tl -> (row block, column tile)
 
-    for (int c = threadIdx.x; c < N; c += LT_THREADS) bias_s[c] = bias ? bias[c] : 0.0f;
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_w);
         for (int s = 0; s < LT_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -133,6 +132,7 @@ linear_act_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         // ===================== epilogue: bias + GELU + store =====================
         const int e = warp - 4, q = e & 3, part = e >> 2;                    // (warp % 4) == q: the TMEM lane quarter it may read
         uint8_t* stg = stg_all + e * LT_STG;
+        float* bias_s = bias_all + e * 64;
         for (int tl = 0; tl < ntl; ++tl) {
             const int buf = tl & 1, jt = tl % n_tiles;
             const int row0 = ((int)blockIdx.x + (tl / n_tiles) * (int)gridDim.x) * LT_BM + q * 32;   // first row of this warp
@@ -140,28 +140,37 @@ linear_act_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256);
 #pragma unroll 1
-            for (int c = part; c < BN / 32; c += LT_EPI_PARTS) {
-                const int n0 = jt * BN + c * 32;
+            for (int c = part; c < BN / 64; c += LT_EPI_PARTS) {             // 64-column chunks: a row leaves as one 128-byte line
+                const int n0 = jt * BN + c * 64;
                 if (n0 >= N) break;                                           // N % 32 == 0 (host-checked)
-                float v[32];
-                tmem_ld32(taddr + (uint32_t)(c * 32), v);
-                uint32_t pk[16];
-#pragma unroll
-                for (int t = 0; t < 32; t += 2) {
-                    float2 ab = make_float2(v[t] + bias_s[n0 + t], v[t + 1] + bias_s[n0 + t + 1]);
-                    if (GELU) ab = gelu_erf2(ab);
-                    if (BF16) { const __nv_bfloat162 h = __floats2bfloat162_rn(ab.x, ab.y); pk[t / 2] = *reinterpret_cast<const uint32_t*>(&h); }
-                    else { const __half2 h = __floats2half2_rn(ab.x, ab.y); pk[t / 2] = *reinterpret_cast<const uint32_t*>(&h); }
-                }
-#pragma unroll
-                for (int s4 = 0; s4 < 4; ++s4)
-                    *reinterpret_cast<uint4*>(stg + lane * LT_STG_PITCH + s4 * 16) = make_uint4(pk[4 * s4], pk[4 * s4 + 1], pk[4 * s4 + 2], pk[4 * s4 + 3]);
+                bias_s[lane] = (bias && n0 + lane < N) ? __ldg(bias + n0 + lane) : 0.0f;
+                bias_s[32 + lane] = (bias && n0 + 32 + lane < N) ? __ldg(bias + n0 + 32 + lane) : 0.0f;
                 __syncwarp();
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {                                  // lane -> (row lane/4 + 8 i, 16-byte piece lane % 4)
-                    const int r = (lane >> 2) + 8 * i, piece = lane & 3;
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int nh = n0 + hh * 32;
+                    if (nh >= N) break;
+                    float v[32];
+                    tmem_ld32(taddr + (uint32_t)(c * 64 + hh * 32), v);
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int t = 0; t < 32; t += 2) {
+                        float2 ab = make_float2(v[t] + bias_s[hh * 32 + t], v[t + 1] + bias_s[hh * 32 + t + 1]);
+                        if (GELU) ab = gelu_erf2(ab);
+                        if (BF16) { const __nv_bfloat162 h = __floats2bfloat162_rn(ab.x, ab.y); pk[t / 2] = *reinterpret_cast<const uint32_t*>(&h); }
+                        else { const __half2 h = __floats2half2_rn(ab.x, ab.y); pk[t / 2] = *reinterpret_cast<const uint32_t*>(&h); }
+                    }
+#pragma unroll
+                    for (int s4 = 0; s4 < 4; ++s4)
+                        *reinterpret_cast<uint4*>(stg + lane * LT_STG_PITCH + hh * 64 + s4 * 16) =
+                            make_uint4(pk[4 * s4], pk[4 * s4 + 1], pk[4 * s4 + 2], pk[4 * s4 + 3]);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {                                  // lane -> (row lane/8 + 4 i, 16-byte piece lane % 8)
+                    const int r = (lane >> 3) + 4 * i, piece = lane & 7;
                     const uint4 val = *reinterpret_cast<const uint4*>(stg + r * LT_STG_PITCH + piece * 16);
-                    if (row0 + r < M)
+                    if (row0 + r < M && n0 + piece * 8 < N)
                         *reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(out) + (int64_t)(row0 + r) * N + n0 + piece * 8) = val;
                 }
                 __syncwarp();
@@ -176,10 +185,10 @@ linear_act_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-template <int BN, bool GELU, bool BF16>
-static int linear_launch(const void* A, const void* W, const float* bias, void* out, int64_t M, int64_t N, int64_t K,
-                         cudaStream_t st) {
-    using Cfg = LtCfg<BN>;
+template <int BN, bool GELU, bool BF16, int LT_STAGES>
+static int linear_launch_s(const void* A, const void* W, const float* bias, void* out, int64_t M, int64_t N, int64_t K,
+                           cudaStream_t st) {
+    using Cfg = LtCfg<BN, LT_STAGES>;
     CUtensorMap ma, mw;
     const int dt = BF16 ? XP_BF16 : XP_F16;
     const uint64_t adims[2] = {(uint64_t)K, (uint64_t)M}, wdims[2] = {(uint64_t)K, (uint64_t)N};
@@ -188,13 +197,20 @@ static int linear_launch(const void* A, const void* W, const float* bias, void* 
     int rc;
     if ((rc = make_tensor_map(&ma, dt, 2, A, adims, strides, abox, 1))) return rc;
     if ((rc = make_tensor_map(&mw, dt, 2, W, wdims, strides, wbox, 1))) return rc;
-    const int smem = Cfg::SMEM_FIXED + (int)N * 4;
-    auto kern = linear_act_tc_kernel<BN, GELU, BF16>;
+    const int smem = Cfg::SMEM;
+    auto kern = linear_act_tc_kernel<BN, GELU, BF16, LT_STAGES>;
     XP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int64_t n_mb = ceil_div(M, LT_BM);
     kern<<<(unsigned)(n_mb < num_sms() ? n_mb : num_sms()), LT_THREADS, smem, st>>>(ma, mw, bias, out, (int)M, (int)N, (int)K);
     XP_LAUNCH_CHECK("linear_act_tc_kernel");
     return XP_OK;
+}
+
+template <int BN, bool GELU, bool BF16>
+static int linear_launch(const void* A, const void* W, const float* bias, void* out, int64_t M, int64_t N, int64_t K,
+                         cudaStream_t st) {
+    static_assert(LtCfg<BN, 4>::SMEM <= 227 * 1024, "four stages + epilogue buffers must fit one CTA");
+    return linear_launch_s<BN, GELU, BF16, 4>(A, W, bias, out, M, N, K, st);
 }
 
 }  // namespace xp

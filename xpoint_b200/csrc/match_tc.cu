@@ -21,9 +21,9 @@
 //            (M=128, N=256, K=8) per k-block into one of two 256-column TMEM accumulators;
 //            tcgen05.commit releases the smem stage / publishes the accumulator.
 //   warp 2   TMEM allocation (512 columns) and release.
-//   warps 4-11 epilogue: thread = accumulator row, two warps per TMEM lane quarter take alternate 32-column chunks;
+//   warps 4-11 epilogue: thread = accumulator row, four warps per TMEM lane quarter take every fourth 32-column chunk;
 //            tcgen05.ld 32 columns at a time, key = |y_j|^2 - 2 acc, running (min, argmin) in registers (ascending j,
-//            strict <: lowest index wins ties), the two halves of a row are merged through shared memory at the end.
+//            strict <: lowest index wins ties), the partial minima of a row are merged through shared memory at the end.
 // The column arg-min  nn_y[j] = argmin_i ( |x_i|^2 - 2 <x_i, y_j> )  comes out of the SAME accumulator tile (the
 // similarity GEMM runs once, not twice): per column the 32 rows of a warp are reduced with two REDUX.MIN
 // (order-preserving uint key, then the lowest row holding it), lane t keeps column t, and one 64-bit
@@ -43,8 +43,8 @@ constexpr int TC_BK16 = 64;                                  // fp16 operands
 constexpr int TC_STAGES = 2;
 constexpr int TC_X_TILE = TC_BM * 128, TC_Y_TILE = TC_BN * 128;
 constexpr int TC_STAGE_BYTES = 2 * TC_X_TILE + 2 * TC_Y_TILE;  // 96 KiB
-constexpr int TC_EPI_WARPS = 8, TC_THREADS = (4 + TC_EPI_WARPS) * 32;
-constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 2 * TC_BN * 4 + 1024 /*align*/ + 128 /*barriers + tmem ptr*/ + 2 * TC_BM * 8 /*row merge*/;
+constexpr int TC_EPI_WARPS = 16, TC_EPI_PARTS = TC_EPI_WARPS / 4, TC_THREADS = (4 + TC_EPI_WARPS) * 32;
+constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 2 * TC_BN * 4 + 1024 /*align*/ + 128 /*barriers + tmem ptr*/ + TC_EPI_PARTS * TC_BM * 8 /*row merge*/;
 
 // ---------------------------------------------------------------------------------- hi / lo split
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi,
@@ -109,7 +109,7 @@ nn_argmin_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_co
     uint64_t* tempty = bars + 2 * TC_STAGES + 2; // [2]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
     float* mrg_key = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 128);     // [2][TC_BM] row arg-min of each column half
-    int* mrg_idx = reinterpret_cast<int*>(mrg_key + 2 * TC_BM);
+    int* mrg_idx = reinterpret_cast<int*>(mrg_key + TC_EPI_PARTS * TC_BM);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pair = blockIdx.y;
@@ -197,18 +197,18 @@ nn_argmin_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_co
             unsigned long long* ck = colkey ? colkey + (int64_t)pair * y_stride : nullptr;
             for (int jt = 0; jt < n_tiles; ++jt) {
                 const int buf = jt & 1;
-                // stage |y_j|^2 of this column tile (256 epilogue threads, one value each)
+                // stage |y_j|^2 of this column tile (the first 256 epilogue threads, one value each)
                 const int et = threadIdx.x - 128;
-                {
+                if (et < TC_BN) {
                     const int j = jt * TC_BN + et;
                     yn_s[buf * TC_BN + et] = j < n_y ? yn[j] : INFINITY;
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" :: "n"(TC_EPI_WARPS * 32) : "memory");
                 mbar_wait(&tfull[buf], (uint32_t)((jt >> 1) & 1));
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TC_BN);
 #pragma unroll 1
-                for (int c = part; c < TC_BN / 32; c += 2) {
+                for (int c = part; c < TC_BN / 32; c += TC_EPI_PARTS) {
                     float v[32];
                     tmem_ld32(taddr + (uint32_t)(c * 32), v);
 #pragma unroll
@@ -234,14 +234,17 @@ nn_argmin_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_co
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[buf]);
             }
-            // merge the two column halves of every row: smaller key, then lower index (the rule of a single ascending scan)
+            // merge the column parts of every row: smaller key, then lower index (the rule of a single ascending scan)
             mrg_key[part * TC_BM + row] = best;
             mrg_idx[part * TC_BM + row] = bestj;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" :: "n"(TC_EPI_WARPS * 32) : "memory");
             if (part == 0 && i0 + row < n_x) {
-                const float k1 = mrg_key[TC_BM + row];
-                const int j1 = mrg_idx[TC_BM + row];
-                if (k1 < best || (k1 == best && j1 < bestj)) bestj = j1;
+#pragma unroll
+                for (int pp = 1; pp < TC_EPI_PARTS; ++pp) {
+                    const float k1 = mrg_key[pp * TC_BM + row];
+                    const int j1 = mrg_idx[pp * TC_BM + row];
+                    if (k1 < best || (k1 == best && j1 < bestj)) { best = k1; bestj = j1; }
+                }
                 nn[(int64_t)pair * x_stride + i0 + row] = bestj;
             }
         }

@@ -12,13 +12,15 @@
 //   3. the hypothesis with the most inliers wins (ties: lowest hypothesis index)
 //   4. two local-optimisation rounds: least-squares DLT over the current inliers (8x8 normal equations, fp64), re-score
 //   5. H is de-normalised and scaled to H[2][2] = 1 (as OpenCV returns it)
-// One CTA per pair; fp64 throughout (a B200 does the 2 G fp64 operations of a 64-pair batch in well under a millisecond, and
+// HG_SLICES CTAs per pair score disjoint hypothesis ranges (64-bit atomicMax on a per-pair key); the last CTA of a pair to
+// finish runs the local optimisation.  fp64 throughout (a B200 does the 2 G fp64 operations of a 64-pair batch in well under a millisecond, and
 // CPU / GPU then agree on every inlier decision).
 #include "common.cuh"
 
 namespace xp {
 
 constexpr int HG_THREADS = 256;
+constexpr int HG_SLICES = 8;          // CTAs per pair in the hypothesis phase (the last one to finish does the refinement)
 
 __host__ __device__ __forceinline__ uint32_t hg_mix(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
@@ -89,7 +91,10 @@ __global__ void __launch_bounds__(HG_THREADS) homography_kernel(const HomParams 
     __shared__ double hcur[8];
     __shared__ int ok_s;
     __shared__ double red[HG_THREADS / 32][45];
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const int b = blockIdx.x, slice = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    // scratch inside the outputs until the last CTA overwrites them: the winning key in H[b][0], the arrival count in n_inl[b]
+    unsigned long long* gkey = reinterpret_cast<unsigned long long*>(p.H + (int64_t)b * 9);
+    __shared__ int last_s;
     const int32_t* kp1 = p.kp1 + (int64_t)b * p.k * 2;
     const int32_t* kp2 = p.kp2 + (int64_t)b * p.k * 2;
     const int32_t* mi = p.match_idx + (int64_t)b * p.k;
@@ -118,19 +123,11 @@ __global__ void __launch_bounds__(HG_THREADS) homography_kernel(const HomParams 
         for (int w = 0; w < HG_THREADS / 32; ++w) base += warp_cnt[w];
         __syncthreads();
     }
-    if (inl)
-        for (int i = tid; i < p.k; i += HG_THREADS) inl[i] = 0;
     const int m = base;
     if (tid == 0) { best_key = 0ull; ok_s = 0; }
     __syncthreads();
-    if (m < 4) {                                       // the reference returns H_est = None here (evaluation.py:364-366)
-        if (tid < 9) p.H[(int64_t)b * 9 + tid] = 0.0;
-        if (tid == 0) p.n_inl[b] = -1;
-        return;
-    }
-
-    // ---- 2./3. hypotheses
-    for (int t = tid; t < p.iters; t += HG_THREADS) {
+    // ---- 2./3. hypotheses of this slice (m < 4: none -- the reference returns H_est = None, evaluation.py:364-366)
+    for (int t = slice * HG_THREADS + tid; t < p.iters && m >= 4; t += HG_SLICES * HG_THREADS) {
         int s[4];
         if (!hg_sample(p.seed, (uint32_t)b, (uint32_t)t, m, s)) continue;
         double a[8][9], h[8];
@@ -149,7 +146,17 @@ __global__ void __launch_bounds__(HG_THREADS) homography_kernel(const HomParams 
     }
     __syncthreads();
     if (tid == 0) {
-        const unsigned long long key = best_key;
+        if (best_key) atomicMax(gkey, best_key);
+        __threadfence();
+        last_s = atomicAdd(p.n_inl + b, 1) == HG_SLICES - 1;     // the counter was zeroed by the host wrapper
+    }
+    __syncthreads();
+    if (!last_s) return;
+    __threadfence();
+    if (inl)
+        for (int i = tid; i < p.k; i += HG_THREADS) inl[i] = 0;
+    if (tid == 0) {
+        const unsigned long long key = *reinterpret_cast<volatile unsigned long long*>(gkey);
         if ((key >> 32) >= 4) {
             const uint32_t t = 0xffffffffu - (uint32_t)(key & 0xffffffffull);
             int s[4];
@@ -280,7 +287,10 @@ extern "C" int xp_estimate_homography(const int32_t* kp1, const int32_t* kp2, co
     p.thr2n = ((double)reproj_threshold / s) * ((double)reproj_threshold / s);
     const int smem = (int)k * 20;
     XP_CUDA_OK(cudaFuncSetAttribute(homography_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    homography_kernel<<<(unsigned)B, HG_THREADS, smem, (cudaStream_t)stream>>>(p);
+    // per-pair scratch lives in the outputs (see the kernel): winning key in H[b][0], arrival counter in n_inliers[b]
+    XP_CUDA_OK(cudaMemsetAsync(H, 0, sizeof(double) * 9 * B, (cudaStream_t)stream));
+    XP_CUDA_OK(cudaMemsetAsync(n_inliers, 0, sizeof(int32_t) * B, (cudaStream_t)stream));
+    homography_kernel<<<dim3((unsigned)B, HG_SLICES), HG_THREADS, smem, (cudaStream_t)stream>>>(p);
     XP_LAUNCH_CHECK("homography_kernel");
     return XP_OK;
 }

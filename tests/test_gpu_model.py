@@ -186,3 +186,30 @@ def test_config5_highres_pair_runs_and_agrees():
         assert outs[True][k].shape == outs[False][k].shape
         assert_close(outs[True][k].float().cpu().numpy(), outs[False][k].float().cpu().numpy(), 1e-2, "config 5 " + k)
     assert outs[True]["prob"].shape == (1, 1, 1024, 1280) and outs[True]["desc"].shape == (1, 256, 128, 160)
+
+
+def test_graphed_pipeline_replays_the_eager_step():
+    """PairPipeline.capture: the CUDA-graph replay returns exactly what the eager step returns, also
+    for new images loaded into the graph's static inputs."""
+    import xpoint_b200 as X
+    torch.manual_seed(0)
+    net = X.XPoint({"takes_pair": True, "mixed_precision": True, "use_attention": {"preset": "E"}}).to(DEV).eval()
+    pipe = X.PairPipeline(net, keep_top_k=512, estimate_homography=True)
+    g = torch.Generator().manual_seed(1)
+    o1, t1 = torch.rand(2, 1, 128, 160, generator=g).to(DEV), torch.rand(2, 1, 128, 160, generator=g).to(DEV)
+    o2, t2 = torch.rand(2, 1, 128, 160, generator=g).to(DEV), torch.rand(2, 1, 128, 160, generator=g).to(DEV)
+    graphed = pipe.capture(o1, t1)
+    assert isinstance(graphed, X.GraphedPairPipeline)
+    for o, t in ((o1, t1), (o2, t2), (o1, t1)):
+        ref = pipe(o, t)
+        got = graphed(o, t)
+        torch.cuda.synchronize()
+        for name, a, b in zip(ref._fields, ref, got):
+            if name.startswith("kp_"):          # keypoint rows past the count are undefined (uninitialised memory)
+                n = ref.n_optical if name == "kp_optical" else ref.n_thermal
+                for i in range(a.shape[0]):
+                    assert torch.equal(a[i, : int(n[i])], b[i, : int(n[i])]), f"graph replay differs in {name}"
+            else:
+                assert torch.equal(a, b), f"graph replay differs from the eager step in {name}"
+    with pytest.raises(RuntimeError):
+        pipe.capture(o1.cpu(), t1.cpu())

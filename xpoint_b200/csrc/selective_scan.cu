@@ -519,32 +519,61 @@ __device__ __forceinline__ void lanes_consumer(const ScanParams& p, uint8_t* bas
         auto body = [&](auto full_tag) {
             constexpr bool FULL = decltype(full_tag)::value;
             float y[C], lw[C];
+            if constexpr (FAST) {
+                // 16-bit inputs: the per-token arithmetic that is independent between neighbouring tokens runs on packed
+                // fp32 pairs (FFMA2 / FMUL2 / FADD2: two IEEE operations per issue slot, bit-identical to the scalar forms)
+                const float2 kl2 = make_float2(kLog2e, kLog2e), kb2 = make_float2(kb, kb), one2 = make_float2(1.0f, 1.0f);
+                const float2 kD2 = make_float2(kD, kD);
 #pragma unroll
-            for (int j = 0; j < C; ++j) {
-                float l;
-                if constexpr (FAST) {                    // l = log2e * softplus(delta + bias)
-                    const float t = fmaf(dv[j], kLog2e, kb);
-                    l = fmaxf(lg2_approx(1.0f + ex2_approx(fminf(t, 100.0f))), t);
-                } else {
-                    const float d = dv[j] + kb;
-                    l = SOFTPLUS ? softplus_f(d) : d;
+                for (int j = 0; j < C; j += 2) {
+                    const float2 t2 = fma2(make_float2(dv[j], dv[j + 1]), kl2, kb2);      // log2e * (delta + bias)
+                    const float2 s2 = add2(make_float2(ex2_approx(fminf(t2.x, 100.0f)), ex2_approx(fminf(t2.y, 100.0f))), one2);
+                    float2 l2 = make_float2(fmaxf(lg2_approx(s2.x), t2.x), fmaxf(lg2_approx(s2.y), t2.y));   // log2e * softplus
+                    float2 u2 = make_float2(uv[j], uv[j + 1]);
+                    if (!FULL) {                                                          // identity steps past the end
+                        if (j >= nv) { l2.x = 0.0f; u2.x = 0.0f; }
+                        if (j + 1 >= nv) { l2.y = 0.0f; u2.y = 0.0f; }
+                    }
+                    const float2 y2 = mul2(kD2, u2);
+                    u2 = mul2(u2, l2);
+                    lw[j] = l2.x; lw[j + 1] = l2.y;
+                    y[j] = y2.x; y[j + 1] = y2.y;
+                    uv[j] = u2.x; uv[j + 1] = u2.y;
                 }
-                if (!FULL && j >= nv) { l = 0.0f; uv[j] = 0.0f; }   // identity step past the end
-                lw[j] = l;
-                y[j] = kD * uv[j];
-                uv[j] *= l;
+            } else {
+#pragma unroll
+                for (int j = 0; j < C; ++j) {
+                    const float d = dv[j] + kb;
+                    float l = SOFTPLUS ? softplus_f(d) : d;
+                    if (!FULL && j >= nv) { l = 0.0f; uv[j] = 0.0f; }   // identity step past the end
+                    lw[j] = l;
+                    y[j] = kD * uv[j];
+                    uv[j] *= l;
+                }
             }
 #pragma unroll
             for (int n = 0; n < NST; ++n) {
                 const float kA = kc[n], hc = kc[NST + 2 + n];
                 float hl[C], pl[C];
                 float P = 1.0f, S_ = 0.0f;
+                if constexpr (FAST) {
+                    const float2 kA2 = make_float2(kA, kA);
 #pragma unroll
-                for (int j = 0; j < C; ++j) {
-                    const float a = ex2_approx(lw[j] * kA);
-                    S_ = fmaf(a, S_, uv[j] * Bv[n][j]);
-                    P *= a;
-                    hl[j] = S_; pl[j] = P;
+                    for (int j = 0; j < C; j += 2) {
+                        const float2 x2 = mul2(make_float2(lw[j], lw[j + 1]), kA2);
+                        const float2 b2 = mul2(make_float2(uv[j], uv[j + 1]), make_float2(Bv[n][j], Bv[n][j + 1]));
+                        const float a0 = ex2_approx(x2.x), a1 = ex2_approx(x2.y);
+                        S_ = fmaf(a0, S_, b2.x); P *= a0; hl[j] = S_; pl[j] = P;
+                        S_ = fmaf(a1, S_, b2.y); P *= a1; hl[j + 1] = S_; pl[j + 1] = P;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < C; ++j) {
+                        const float a = ex2_approx(lw[j] * kA);
+                        S_ = fmaf(a, S_, uv[j] * Bv[n][j]);
+                        P *= a;
+                        hl[j] = S_; pl[j] = P;
+                    }
                 }
                 // warp-level inclusive scan of the affine maps h -> P*h + S across the 32 lane chunks
 #pragma unroll
@@ -555,8 +584,18 @@ __device__ __forceinline__ void lanes_consumer(const ScanParams& p, uint8_t* bas
                 float Pe = __shfl_up_sync(0xffffffffu, P, 1), Se = __shfl_up_sync(0xffffffffu, S_, 1);
                 if (lane == 0) { Pe = 1.0f; Se = 0.0f; }
                 const float hin = fmaf(Pe, hc, Se);
+                if constexpr (FAST) {
+                    const float2 hin2 = make_float2(hin, hin);
 #pragma unroll
-                for (int j = 0; j < C; ++j) y[j] = fmaf(fmaf(pl[j], hin, hl[j]), Cv[n][j], y[j]);
+                    for (int j = 0; j < C; j += 2) {
+                        const float2 h2 = fma2(make_float2(pl[j], pl[j + 1]), hin2, make_float2(hl[j], hl[j + 1]));
+                        const float2 y2 = fma2(h2, make_float2(Cv[n][j], Cv[n][j + 1]), make_float2(y[j], y[j + 1]));
+                        y[j] = y2.x; y[j + 1] = y2.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < C; ++j) y[j] = fmaf(fmaf(pl[j], hin, hl[j]), Cv[n][j], y[j]);
+                }
                 if (lane == 31) sts32(rcs + (r * RCF + NST + 2 + n) * 4, fmaf(P, hc, S_));
             }
             if constexpr (HAS_Z) {

@@ -300,6 +300,8 @@ XP_API int xp_mnn_match(const float* d1, const float* d2, const int32_t* n1, con
  *   kp1, kp2 (B, k, 2) int32 (y, x); n1 (B) int32 valid rows of kp1 (NULL = k); match_idx (B, k) int32: row of kp2 matched
  *   to kp1 row i, or -1.  H (B, 3, 3) fp64 row-major with H[2][2] = 1; inlier_mask (B, k) u8 per kp1 row (nullable);
  *   n_inliers (B) int32, -1 when fewer than 4 matches / no valid hypothesis (the reference's H_est = None; H is 0 then).
+ *   At most 11 264 matches per pair take part (the first ones in kp1 order); XPoint's 4 096 / 16 384-keypoint configurations
+ *   stay below that.
  */
 XP_API int xp_estimate_homography(const int32_t* kp1, const int32_t* kp2, const int32_t* n1, const int32_t* match_idx,
                                   int64_t B, int64_t k, int64_t height, int64_t width, int32_t iters, float reproj_threshold,

@@ -287,7 +287,7 @@ def _hom_inputs(seed, B, k, Hh, Ww, outliers):
     return kp1, kp2, mi, n1
 
 
-@pytest.mark.parametrize("B,k,outliers", [(3, 1024, 0.3), (2, 4096, 0.6), (4, 200, 0.1)])
+@pytest.mark.parametrize("B,k,outliers", [(3, 1024, 0.3), (2, 4096, 0.6), (4, 200, 0.1), (1, 16384, 0.4), (1, 20000, 0.2)])
 def test_homography_vs_oracle(B, k, outliers):
     """xp_estimate_homography against its oracle restatement: same winning inlier set (the fp64 arithmetic of hypothesis
     scoring is identical on both sides), H to 1e-8 (the least-squares sums are added in a different order)."""
@@ -302,7 +302,7 @@ def test_homography_vs_oracle(B, k, outliers):
         assert int(r.n_inliers[b]) == cnt
         assert np.array_equal(r.inliers[b].cpu().numpy(), inl)
         np.testing.assert_allclose(r.H[b].cpu().numpy(), H, rtol=1e-8, atol=1e-8)
-        assert cnt >= 0.5 * (1 - outliers) * (mi[b, : n1[b]] >= 0).sum()
+        assert cnt >= 0.5 * (1 - outliers) * min((mi[b, : n1[b]] >= 0).sum(), 11264)
 
 
 def test_homography_golden_and_degenerate():

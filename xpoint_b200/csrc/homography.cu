@@ -20,6 +20,7 @@
 namespace xp {
 
 constexpr int HG_THREADS = 256;
+constexpr int HG_MAX_MATCHES = 11264;  // matches held in shared memory (20 B each); later ones (keypoint order) are not used
 constexpr int HG_SLICES = 8;          // CTAs per pair in the hypothesis phase (the last one to finish does the refinement)
 
 __host__ __device__ __forceinline__ uint32_t hg_mix(uint32_t x) {
@@ -77,15 +78,15 @@ __device__ __forceinline__ double hg_err2(const double* h, double x, double y, d
 struct HomParams {
     const int32_t* kp1; const int32_t* kp2; const int32_t* n1; const int32_t* match_idx;
     double* H; uint8_t* inlier; int32_t* n_inl;
-    int k, iters, lo_rounds; uint32_t seed;
+    int k, cap, iters, lo_rounds; uint32_t seed;      // cap = min(k, HG_MAX_MATCHES): capacity of the match arrays
     double cx, cy, inv_s, thr2n;       // normalisation x' = (x - cx) * inv_s; squared threshold in normalised units
 };
 
 __global__ void __launch_bounds__(HG_THREADS) homography_kernel(const HomParams p) {
     extern __shared__ __align__(16) uint8_t hg_smem[];
     float* px = reinterpret_cast<float*>(hg_smem);          // [k] normalised source / target coordinates of match j
-    float* py = px + p.k; float* qx = py + p.k; float* qy = qx + p.k;
-    int* src = reinterpret_cast<int*>(qy + p.k);            // [k] keypoint index of match j
+    float* py = px + p.cap; float* qx = py + p.cap; float* qy = qx + p.cap;
+    int* src = reinterpret_cast<int*>(qy + p.cap);          // [cap] keypoint index of match j
     __shared__ int warp_cnt[HG_THREADS / 32 + 1];
     __shared__ unsigned long long best_key;
     __shared__ double hcur[8];
@@ -112,8 +113,8 @@ __global__ void __launch_bounds__(HG_THREADS) homography_kernel(const HomParams 
         __syncthreads();
         int off = base;
         for (int w = 0; w < wrp; ++w) off += warp_cnt[w];
-        if (has) {
-            const int j = off + __popc(bal & ((1u << lane) - 1u));
+        const int j = off + __popc(bal & ((1u << lane) - 1u));
+        if (has && j < p.cap) {
             px[j] = (float)(((double)kp1[2 * i + 1] - p.cx) * p.inv_s);      // (x, y) = (kp[1], kp[0])
             py[j] = (float)(((double)kp1[2 * i] - p.cy) * p.inv_s);
             qx[j] = (float)(((double)kp2[2 * j2 + 1] - p.cx) * p.inv_s);
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(HG_THREADS) homography_kernel(const HomParams 
         for (int w = 0; w < HG_THREADS / 32; ++w) base += warp_cnt[w];
         __syncthreads();
     }
-    const int m = base;
+    const int m = min(base, p.cap);
     if (tid == 0) { best_key = 0ull; ok_s = 0; }
     __syncthreads();
     // ---- 2./3. hypotheses of this slice (m < 4: none -- the reference returns H_est = None, evaluation.py:364-366)
@@ -275,17 +276,17 @@ extern "C" int xp_estimate_homography(const int32_t* kp1, const int32_t* kp2, co
                                       int32_t lo_rounds, uint32_t seed, double* H, uint8_t* inlier_mask, int32_t* n_inliers,
                                       xp_stream_t stream) {
     XP_REQUIRE(kp1 && kp2 && match_idx && H && n_inliers, "xp_estimate_homography: NULL tensor pointer");
-    XP_REQUIRE(B >= 0 && B <= 65535 && k > 0 && k <= 8192, "xp_estimate_homography: need 0 <= B <= 65535, 0 < k <= 8192");
+    XP_REQUIRE(B >= 0 && B <= 65535 && k > 0 && k <= (1 << 20), "xp_estimate_homography: need 0 <= B <= 65535, 0 < k <= 2^20");
     XP_REQUIRE(height > 0 && width > 0 && iters > 0 && iters <= (1 << 20) && reproj_threshold > 0.0f && lo_rounds >= 0 && lo_rounds <= 16,
                "xp_estimate_homography: bad parameters");
     if (B == 0) return XP_OK;
     HomParams p;
     p.kp1 = kp1; p.kp2 = kp2; p.n1 = n1; p.match_idx = match_idx; p.H = H; p.inlier = inlier_mask; p.n_inl = n_inliers;
-    p.k = (int)k; p.iters = iters; p.lo_rounds = lo_rounds; p.seed = seed;
+    p.k = (int)k; p.cap = (int)(k < HG_MAX_MATCHES ? k : HG_MAX_MATCHES); p.iters = iters; p.lo_rounds = lo_rounds; p.seed = seed;
     const double s = 0.5 * (double)(height > width ? height : width);
     p.cx = 0.5 * (double)width; p.cy = 0.5 * (double)height; p.inv_s = 1.0 / s;
     p.thr2n = ((double)reproj_threshold / s) * ((double)reproj_threshold / s);
-    const int smem = (int)k * 20;
+    const int smem = p.cap * 20;
     XP_CUDA_OK(cudaFuncSetAttribute(homography_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     // per-pair scratch lives in the outputs (see the kernel): winning key in H[b][0], arrival counter in n_inliers[b]
     XP_CUDA_OK(cudaMemsetAsync(H, 0, sizeof(double) * 9 * B, (cudaStream_t)stream));

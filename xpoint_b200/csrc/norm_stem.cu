@@ -102,6 +102,117 @@ __global__ void __launch_bounds__(256) add_layer_norm_kernel(const AddLnParams p
     }
 }
 
+
+// ---- compile-time specialisation of the kernel above for the combinations the XPoint encoder issues (18 launches per
+// step): dtypes, lanes per row and the presence of every optional operand are template parameters, chunk indices are 32-bit.
+// The generic kernel spends 33 instructions per element on run-time dtype dispatch, 64-bit indexing and rolled shuffle
+// loops and is issue-bound (76 % busy, ncu); this one is bound by its four memory streams.
+template <int DT> __device__ __forceinline__ float4 ld4_t(const void* p, int i4) {
+    if constexpr (DT == XP_F32) return __ldg(reinterpret_cast<const float4*>(p) + i4);
+    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p) + i4);
+    if constexpr (DT == XP_F16) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+        return make_float4(a.x, a.y, b.x, b.y);
+    }
+    return make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u), __uint_as_float(raw.y << 16),
+                       __uint_as_float(raw.y & 0xffff0000u));
+}
+template <int DT> __device__ __forceinline__ void st4_t(void* p, int i4, float4 v) {
+    if constexpr (DT == XP_F32) { reinterpret_cast<float4*>(p)[i4] = v; return; }
+    uint2 raw;
+    if constexpr (DT == XP_F16) {
+        *reinterpret_cast<__half2*>(&raw.x) = __floats2half2_rn(v.x, v.y);
+        *reinterpret_cast<__half2*>(&raw.y) = __floats2half2_rn(v.z, v.w);
+    } else {
+        *reinterpret_cast<__nv_bfloat162*>(&raw.x) = __floats2bfloat162_rn(v.x, v.y);
+        *reinterpret_cast<__nv_bfloat162*>(&raw.y) = __floats2bfloat162_rn(v.z, v.w);
+    }
+    reinterpret_cast<uint2*>(p)[i4] = raw;
+}
+
+// XDT: dtype of x; RDT / SDT / YDT: dtype of res / sum_out / y or -1 when absent; BIAS: pre_bias present
+template <int CH, int LPR, int XDT, int RDT, int SDT, int YDT, bool BIAS>
+__global__ void __launch_bounds__(256) add_layer_norm_fast_kernel(const AddLnParams p) {
+    constexpr int RPW = 32 / LPR;
+    const int lane = threadIdx.x & 31, sub = lane & (LPR - 1);
+    const int row = (blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW + lane / LPR;      // rows * C / 4 < 2^31 (host-checked)
+    const bool live = row < (int)p.rows;
+    const int nch = p.C >> 2;
+    const int o4 = row * nch;
+    float4 v[CH];
+    float s = 0.0f;
+#pragma unroll
+    for (int q = 0; q < CH; ++q) {
+        const int c4 = q * LPR + sub;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live && c4 < nch) {
+            t = ld4_t<XDT>(p.x, o4 + c4);
+            if constexpr (RDT >= 0) { const float4 r = ld4_t<RDT>(p.res, o4 + c4); t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w; }
+            if constexpr (BIAS) { const float4 r = __ldg(reinterpret_cast<const float4*>(p.pre_bias) + c4); t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w; }
+            if constexpr (SDT >= 0) st4_t<SDT>(p.sum_out, o4 + c4, t);
+        }
+        v[q] = t;
+        s += (t.x + t.y) + (t.z + t.w);
+    }
+    if constexpr (YDT >= 0) {
+#pragma unroll
+    for (int o = LPR >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)p.C;
+    float ss = 0.0f;
+#pragma unroll
+    for (int q = 0; q < CH; ++q) {
+        if (q * LPR + sub < nch) {
+            v[q].x -= mean; v[q].y -= mean; v[q].z -= mean; v[q].w -= mean;
+            ss = fmaf(v[q].x, v[q].x, fmaf(v[q].y, v[q].y, fmaf(v[q].z, v[q].z, fmaf(v[q].w, v[q].w, ss))));
+        }
+    }
+#pragma unroll
+    for (int o = LPR >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss / (float)p.C + p.eps);
+#pragma unroll
+    for (int q = 0; q < CH; ++q) {
+        const int c4 = q * LPR + sub;
+        if (live && c4 < nch) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma) + c4), b = __ldg(reinterpret_cast<const float4*>(p.beta) + c4);
+            st4_t<YDT>(p.y, o4 + c4, make_float4(fmaf(v[q].x * rstd, g.x, b.x), fmaf(v[q].y * rstd, g.y, b.y),
+                                                                       fmaf(v[q].z * rstd, g.z, b.z), fmaf(v[q].w * rstd, g.w, b.w)));
+        }
+    }
+    }
+}
+
+// launches the specialised kernel if (ch, lpr, dtypes, operands) is one of the encoder's combinations; false otherwise
+template <int XDT, int RDT, int SDT, int YDT, bool BIAS>
+static bool add_ln_fast_shape(const AddLnParams& p, int ch, int lpr, unsigned grid, cudaStream_t st) {
+    if (ch == 3 && lpr == 8) add_layer_norm_fast_kernel<3, 8, XDT, RDT, SDT, YDT, BIAS><<<grid, 256, 0, st>>>(p);
+    else if (ch == 3 && lpr == 16) add_layer_norm_fast_kernel<3, 16, XDT, RDT, SDT, YDT, BIAS><<<grid, 256, 0, st>>>(p);
+    else if (ch == 3 && lpr == 32) add_layer_norm_fast_kernel<3, 32, XDT, RDT, SDT, YDT, BIAS><<<grid, 256, 0, st>>>(p);
+    else if (ch == 6 && lpr == 32) add_layer_norm_fast_kernel<6, 32, XDT, RDT, SDT, YDT, BIAS><<<grid, 256, 0, st>>>(p);
+    else return false;
+    return true;
+}
+template <int LO>   // LO: the 16-bit dtype of the activations (XP_F16 | XP_BF16), or XP_F32 for the fp32 model
+static bool add_ln_fast(const AddLnParams& p, int ch, int lpr, unsigned grid, cudaStream_t st) {
+    const bool has_res = p.res != nullptr, has_sum = p.sum_out != nullptr, has_y = p.y != nullptr, has_bias = p.pre_bias != nullptr;
+    if (p.x_dt != LO) return false;
+    if constexpr (LO == XP_F32) {
+        // LayerNorm of the fp32 residual stream into the activation dtype: the first norm of a stage
+        if (!has_res && !has_sum && has_y && !has_bias && p.y_dt == XP_F16) return add_ln_fast_shape<XP_F32, -1, -1, XP_F16, false>(p, ch, lpr, grid, st);
+        if (!has_res && !has_sum && has_y && !has_bias && p.y_dt == XP_BF16) return add_ln_fast_shape<XP_F32, -1, -1, XP_BF16, false>(p, ch, lpr, grid, st);
+    }
+    // x + res -> sum (fp32) and LayerNorm -> y (activation dtype): every VSSBlock branch
+    if (has_res && p.res_dt == XP_F32 && has_sum && p.sum_dt == XP_F32 && has_y && p.y_dt == LO && !has_bias)
+        return add_ln_fast_shape<LO, XP_F32, XP_F32, LO, false>(p, ch, lpr, grid, st);
+    // conv output + bias -> LayerNorm -> fp32 residual stream: patch-embed / downsample tails
+    if (!has_res && !has_sum && has_y && p.y_dt == XP_F32 && has_bias)
+        return add_ln_fast_shape<LO, -1, -1, XP_F32, true>(p, ch, lpr, grid, st);
+    // x + res -> sum in the activation dtype, no norm: the residual sum in front of a downsample convolution
+    if (has_res && p.res_dt == XP_F32 && has_sum && p.sum_dt == LO && !has_y && !has_bias)
+        return add_ln_fast_shape<LO, XP_F32, LO, -1, false>(p, ch, lpr, grid, st);
+    return false;
+}
+
 // scalar fallback (C % 4 != 0 or unaligned pointers): warp per row
 template <int PER>
 __global__ void __launch_bounds__(256) add_layer_norm_scalar_kernel(const AddLnParams p) {
@@ -285,6 +396,14 @@ extern "C" int xp_add_layer_norm(const void* x, const void* res, const float* pr
         while (lpr < 32 && lpr * 3 < nch) lpr <<= 1;          // <= 3 chunks per lane until the warp is one row wide
         const int ch = (nch + lpr - 1) / lpr;
         const unsigned grid = (unsigned)ceil_div(rows, 8 * (32 / lpr));
+        if (rows * nch < ((int64_t)1 << 31) - 8 * 32 * nch) {              // 32-bit chunk indices (incl. the last CTA's dead rows)
+            bool done = x_dtype == XP_F16 ? add_ln_fast<XP_F16>(p, ch, lpr, grid, st)
+                      : x_dtype == XP_BF16 ? add_ln_fast<XP_BF16>(p, ch, lpr, grid, st) : add_ln_fast<XP_F32>(p, ch, lpr, grid, st);
+            if (done) {
+                XP_LAUNCH_CHECK("add_layer_norm_fast_kernel");
+                return XP_OK;
+            }
+        }
         if (ch <= 1) add_layer_norm_kernel<1><<<grid, 256, 0, st>>>(p, lpr);
         else if (ch <= 2) add_layer_norm_kernel<2><<<grid, 256, 0, st>>>(p, lpr);
         else if (ch <= 3) add_layer_norm_kernel<3><<<grid, 256, 0, st>>>(p, lpr);

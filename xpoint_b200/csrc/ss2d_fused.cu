@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(256) ss2d_dt_proj_kernel(const T* __restrict__
     }
 }
 
-// 16-bit inputs with ranks 9..16 (stage 1 of XPoint: dt_rank 12): the 8 tokens x R rank rows of a thread stay PACKED (16-byte
+// 16-bit inputs (all ranks up to 16; XPoint: dt_rank 6, 12): the 8 tokens x R rank rows of a thread stay PACKED (16-byte
 // vectors, R * 4 registers) and feed the mixed-precision FMA of sm_100 (fma.rn.f32.f16 -> FHFMA: 16-bit operands taken
 // from either half of a register, fp32 accumulator, full FFMA rate), so nothing is widened; the (D, R) weights of the
 // group are rounded to the input dtype (what the reference's autocast GEMM multiplies with) and paired in shared memory.
@@ -571,6 +571,7 @@ extern "C" int xp_ss2d_dt_proj(const void* dts_r, const float* weight, void* del
     XP_REQUIRE(B >= 0 && G > 0 && D > 0 && L > 0, "xp_ss2d_dt_proj: bad shape");
     XP_REQUIRE(R >= 1 && (R <= 8 || (R <= 16 && dtype != XP_F32 && D * 8 * 4 <= 48 * 1024)),
                "xp_ss2d_dt_proj: dt_rank must be in 1..8, or 9..16 with 16-bit inputs and D <= 1536 (got %lld)", (long long)R);
+    XP_REQUIRE(R <= 8 || D * 8 * 4 <= 48 * 1024, "xp_ss2d_dt_proj: D too large for ranks above 8");
     XP_REQUIRE(dtype >= XP_F32 && dtype <= XP_BF16, "xp_ss2d_dt_proj: unsupported dtype %d", dtype);
     const int64_t vec = dtype == XP_F32 ? 4 : 8;
     XP_REQUIRE(L % vec == 0 && x_batch_stride % vec == 0 && x_group_stride % vec == 0 && x_rank_stride % vec == 0 &&
@@ -580,15 +581,13 @@ extern "C" int xp_ss2d_dt_proj(const void* dts_r, const float* weight, void* del
     if (B == 0) return XP_OK;
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid((unsigned)ceil_div(L, 256 * vec), (unsigned)(B * G));
-    if (R > 8) {
-        const size_t smem = (size_t)D * 8 * 4;
-        if (dtype == XP_F16)
-            ss2d_dt_proj16_kernel<__half, 8><<<grid, 256, smem, st>>>((const __half*)dts_r, weight, (__half*)delta, (int)G, (int)D,
-                                                                       (int)R, L, x_batch_stride, x_group_stride, x_rank_stride);
-        else
-            ss2d_dt_proj16_kernel<__nv_bfloat16, 8><<<grid, 256, smem, st>>>((const __nv_bfloat16*)dts_r, weight,
-                                                                              (__nv_bfloat16*)delta, (int)G, (int)D, (int)R, L,
-                                                                              x_batch_stride, x_group_stride, x_rank_stride);
+    if (dtype != XP_F32 && D * 8 * 4 <= 48 * 1024) {        // 16-bit inputs: packed operands + mixed-precision FMA (FHFMA)
+#define XP_DT16(T, RP) ss2d_dt_proj16_kernel<T, RP><<<grid, 256, (size_t)D * RP * 4, st>>>((const T*)dts_r, weight, (T*)delta, (int)G, \
+                                                                                            (int)D, (int)R, L, x_batch_stride,     \
+                                                                                            x_group_stride, x_rank_stride)
+        if (dtype == XP_F16) { if (R <= 8) XP_DT16(__half, 4); else XP_DT16(__half, 8); }
+        else { if (R <= 8) XP_DT16(__nv_bfloat16, 4); else XP_DT16(__nv_bfloat16, 8); }
+#undef XP_DT16
         XP_LAUNCH_CHECK("ss2d_dt_proj16_kernel");
         return XP_OK;
     }

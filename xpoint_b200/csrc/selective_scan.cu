@@ -165,7 +165,8 @@ __global__ void __launch_bounds__(GEN_WARPS * 32) scan_generic_kernel(const Scan
 //     below the 16-bit input quantisation.  fp32 inputs keep the series-corrected softplus_f.
 constexpr int LN_STAGES = 4;     // u/delta ring depth per consumer warp
 constexpr int LN_BCS = 2;        // B/C buffer depth per consumer warp
-constexpr int LN_MAXROWS = 8;    // max channel rows per warp
+constexpr int LN_MAXROWS = 32;   // max channel rows per warp (row table size)
+constexpr int LN_DT_ROWS = 8;    // rows per warp with the fused dt_proj (height of its delta tile)
 
 template <typename IN_T> __device__ __forceinline__ void widen16(const uint4& v, float (&f)[16 / sizeof(IN_T)]);
 template <> __device__ __forceinline__ void widen16<float>(const uint4& v, float (&f)[4]) {
@@ -234,7 +235,7 @@ template <int NST, typename IN_T, int C, bool HAS_Z, int NW, bool DTF> struct La
     static constexpr int RCF = NST == 1 ? 4 : 8;                         // floats of per-row constants
     static constexpr int RC_BYTES = LN_MAXROWS * RCF * 4;
     static constexpr int DROW = CHUNK + 16;                              // padded row stride of the dts_r / delta tiles
-    static constexpr int DTILE = LN_MAXROWS * DROW;                      // delta tile: one row per channel row of the warp
+    static constexpr int DTILE = LN_DT_ROWS * DROW;                      // delta tile: one row per channel row of the warp
     static constexpr int NBARS = 2 * LN_STAGES + 2 * LN_BCS + (DTF ? 2 : 0);   // full/empty, bcfull/bcempty [, dfull/dempty]
     // dts_r tile: the rank padded to the MMA's K (8 or 16); R = 0 unless DTF, everything folds to constants then
     __host__ __device__ static constexpr int rpad(int R) { return R <= 8 ? 8 : 16; }
@@ -945,8 +946,10 @@ template <int NST, typename IN_T, typename OUT_T> static int launch_lanes(ScanPa
     const int64_t Dg = p.dim / p.groups;
     // rows per warp: share B/C across as many rows as possible while keeping >= ~2 waves of warps
     const int64_t target_warps = (int64_t)num_sms() * 16 * 2;
-    int rw = LN_MAXROWS;
+    int rw = p.R > 0 ? LN_DT_ROWS : LN_MAXROWS;
     while (rw > 1 && p.batch * p.groups * ceil_div(Dg, rw) < target_warps) rw >>= 1;
+    static const int rw_override = env_int("XP_LANES_RW", 0);   // tuning knob
+    if (rw_override > 0 && rw_override <= (p.R > 0 ? LN_DT_ROWS : LN_MAXROWS)) rw = rw_override;
     p.rows_per_warp = rw;
     const int64_t warps = p.batch * p.groups * ceil_div(Dg, rw);
     // tokens per lane per step: 16 for single-state 16-bit inputs (halves the per-step overhead) unless the

@@ -6,17 +6,18 @@
 // This file is a different decomposition with three kernels, chosen by shape on the host:
 //
 //  * scan_lanes_kernel   (dstate 1|2, the shipped XPoint config; HBM-bound)
-//      a warp owns RW channel rows of one (batch, group) and walks the sequence in steps of 256 tokens:
-//      every lane loads 8 consecutive tokens with 128-bit loads (1 KiB contiguous per row per step, so
-//      DRAM sees long bursts), scans them sequentially in registers, and the 32 lane-chunks are combined
-//      with a warp-shuffle prefix scan over the affine maps (a, b) -> a*h + b.  B/C are loaded once per
-//      step and reused by the RW rows.  The next row's u/delta are prefetched into registers.
-//  * scan_rows_tma_kernel (dstate 4|8|16; MUFU/FP32-issue-bound)
-//      a lane owns one channel row and all its states and runs the recurrence sequentially (one ex2 and
+//      a consumer warp owns up to 32 channel rows of one (batch, group) and walks the sequence in steps of 256 or 512
+//      tokens; a producer warp streams the rows' u / delta chunks (1-D bulk TMA copies) into per-warp shared-memory
+//      rings, B/C once per step.  Every lane scans 8 or 16 consecutive tokens sequentially in registers and the 32
+//      lane chunks are combined with a warp-shuffle prefix scan over the affine maps (a, b) -> a*h + b.
+//      With xp_scan_args.dt_weight (fused dt_proj) delta is not loaded but formed per step from the low-rank dts_r rows
+//      by a tensor-core micro-GEMM (mma.sync) inside the consumer warp.
+//  * scan_rows_kernel    (dstate 4|8|16; MUFU/FP32-issue-bound)
+//      a channel row is owned by two adjacent lanes (states n % 2) that run the recurrences sequentially (one ex2 and
 //      four FP32 ops per (token, state) -- no redundant scan work).  Each warp runs a private TMA pipeline:
-//      u/delta (and z) tiles [32 rows x 128 B] land in 128B-swizzled shared memory, B/C tiles
-//      [dstate x 128 B] are read as broadcasts, y goes back through a swizzled tile and a TMA store.
-//  * scan_generic_kernel  (any dstate <= 256, any alignment / strides, delta groups)
+//      u/delta (and z) tiles [16 rows x 128 B] land in 128B-swizzled shared memory, the CTA shares one ring of B/C tiles
+//      [dstate x 128 B] that are read as broadcasts, y leaves through 32-byte stores per row and step.
+//  * scan_generic_kernel  (any dstate <= 256, any alignment / strides, delta groups, fused dt_proj of any rank)
 //      warp per row, lanes along the sequence, one state at a time, scalar loads.
 //
 // All three keep fp32 state and accumulation (reference: csms6s.py:52-68).

@@ -130,3 +130,15 @@ def test_product_never_touches_the_oracle():
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle" not in text.lower().replace("# no oracle", ""), f"{f} mentions the oracle"
     assert "/root/reference" not in open(os.path.join(ROOT, "bench.py")).read()
+
+
+def test_algorithmic_bytes_formula():
+    """B*L*[(2*KD + 2*K*N)*s_in + KD*s_out] + 4*KD*(N+2); config 2 fp32 = 6.375 GB, bf16->fp32 = 4.194 GB; with
+    the fused dt_proj the delta term KD*s_in becomes K*R*s_in (+ the weights)."""
+    from xpoint_b200.selective_scan import algorithmic_bytes
+    assert abs(algorithmic_bytes(32, 768, 4, 16, 20480, 4, 4) / 1e9 - 6.375) < 1e-3
+    assert abs(algorithmic_bytes(32, 768, 4, 16, 20480, 2, 4) / 1e9 - 4.194) < 1e-3
+    assert abs(algorithmic_bytes(32, 768, 4, 16, 20480, 2, 2) / 1e9 - 3.188) < 1e-3
+    plain = algorithmic_bytes(128, 384, 4, 1, 20480, 2, 4)
+    fused = algorithmic_bytes(128, 384, 4, 1, 20480, 2, 4, dt_rank=6)
+    assert plain - fused == 128 * 20480 * (384 - 4 * 6) * 2 - 384 * 6 * 2

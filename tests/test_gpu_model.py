@@ -213,3 +213,44 @@ def test_graphed_pipeline_replays_the_eager_step():
                 assert torch.equal(a, b), f"graph replay differs from the eager step in {name}"
     with pytest.raises(RuntimeError):
         pipe.capture(o1.cpu(), t1.cpu())
+
+
+@pytest.mark.parametrize("reflection", [True, False])
+def test_heads_respect_reflection_pad(reflection):
+    """with reflection_pad=False the reference builds nn.ZeroPad2d (XPoint.py:101-104); the fused eval heads
+    must pad the same way as the module-by-module path."""
+    import xpoint_b200 as X
+    torch.manual_seed(0)
+    net = X.XPoint({"takes_pair": False, "reflection_pad": reflection, "use_attention": {"preset": "E"}}).to(DEV).eval()
+    img = torch.rand(2, 1, 64, 96, device=DEV)
+    with torch.no_grad():
+        assert net._heads_foldable()
+        fused = net({"image": img})
+        net._heads_foldable = lambda: False
+        plain = net({"image": img})
+    assert type(net.detector_head_convolutions[0]).__name__ == ("ReflectionPad2d" if reflection else "ZeroPad2d")
+    for k in ("prob", "desc", "encoder_output"):
+        assert_close(fused[k].cpu().numpy(), plain[k].cpu().numpy(), 2e-5, f"reflection_pad={reflection} {k}")
+
+
+def test_pipeline_topk_zero_means_no_cap():
+    """keep_top_k = 0 is the reference's "no cap" (utils.py:179 `if keep_top_k > 0`, configs/cipdp.yaml:55 topk: 0)."""
+    import xpoint_b200 as X
+    from oracle import oracle as O
+    g = torch.Generator().manual_seed(3)
+    B, H, W = 1, 128, 160
+    prob = torch.rand(2 * B, 1, H, W, generator=g) ** 6
+    desc = torch.nn.functional.normalize(torch.randn(2 * B, 256, H // 8, W // 8, generator=g), dim=1)
+    mask = (torch.rand(2 * B, 1, H, W, generator=g) > 0.2).float()
+    pipe = X.PairPipeline(None, nms=8, detection_threshold=0.015, keep_top_k=0)
+    for m in (None, mask):
+        r = pipe.tail(prob[:B].to(DEV), prob[B:].to(DEV), desc[:B].to(DEV), desc[B:].to(DEV),
+                      valid_mask_o=None if m is None else m[:B].to(DEV), valid_mask_t=None if m is None else m[B:].to(DEV))
+        for img, kp_t, n_t in ((0, r.kp_optical, r.n_optical), (1, r.kp_thermal, r.n_thermal)):
+            p = prob[img, 0] if m is None else prob[img, 0] * m[img, 0]
+            kp = O.extract_keypoints(O.box_nms(p.numpy(), 8, 0.015, keep_top_k=0), 0.015)
+            assert len(kp) > 100 and int(n_t[0]) == len(kp) <= pipe.capacity(H, W)
+            assert np.array_equal(kp_t[0, :len(kp)].cpu().numpy().astype(np.int64), kp)
+        assert int(r.n_matches[0]) > 0
+    with pytest.raises(ValueError):
+        X.PairPipeline(None, keep_top_k=-1)

@@ -295,3 +295,23 @@ def test_full_size_properties_config2():
     # linearity in u
     out2 = X.selective_scan_fn(u[:4] * 2.0, dl[:4], A, Bm[:4], Cm[:4], D, bias, True, True)
     assert_close(out2.cpu().numpy(), 2.0 * out[:4].cpu().numpy(), 1e-5, "linearity")
+
+
+def test_selective_scan_cuda_backend_output_dtype():
+    """SelectiveScanCuda.apply maps `backend` like csms6s.py:76-85 -- None/'oflex' honour oflex, 'core'/'mamba'
+    return the input dtype, 'torch' is refused (no fallback in this package)."""
+    import xpoint_b200 as X
+    g = torch.Generator().manual_seed(0)
+    u = torch.randn(1, 8, 64, generator=g).half().cuda()
+    dl = torch.rand(1, 8, 64, generator=g).half().cuda()
+    A = -torch.rand(8, 2, generator=g).cuda()
+    Bm = torch.randn(1, 1, 2, 64, generator=g).half().cuda()
+    Cm = torch.randn(1, 1, 2, 64, generator=g).half().cuda()
+    assert X.SelectiveScanCuda.apply(u, dl, A, Bm, Cm, None, None, True, True, None).dtype == torch.float32
+    assert X.SelectiveScanCuda.apply(u, dl, A, Bm, Cm, None, None, True, True, "oflex").dtype == torch.float32
+    assert X.SelectiveScanCuda.apply(u, dl, A, Bm, Cm, None, None, True, False, None).dtype == torch.float16
+    assert X.SelectiveScanCuda.apply(u, dl, A, Bm, Cm, None, None, True, True, "mamba").dtype == torch.float16
+    assert X.SelectiveScanCuda.apply(u, dl, A, Bm, Cm, None, None, True, True, "core").dtype == torch.float16
+    assert X.selective_scan_fn_csms6s(u, dl, A, Bm, Cm, backend="core").dtype == torch.float16
+    with pytest.raises(RuntimeError):
+        X.SelectiveScanCuda.apply(u, dl, A, Bm, Cm, None, None, True, True, "torch")

@@ -352,3 +352,17 @@ def test_pipeline_with_homography():
         assert int(r.n_inliers[b]) == int(r.n_matches[b]) == k          # identical images: every keypoint matches itself
         assert torch.allclose(r.H[b], eye, atol=1e-9)
     del prob_t
+
+
+@pytest.mark.parametrize("C", [48, 100, 2048])
+def test_get_matches_any_descriptor_size(C):
+    """descriptor sizes outside the tensor-core kernel's range (C % 32, C <= 1024) take the fp32 kernels instead
+    of raising; the reference's get_matches accepts any descriptor_size."""
+    import xpoint_b200 as X
+    from oracle import oracle as O
+    g = torch.Generator().manual_seed(C)
+    d1 = torch.nn.functional.normalize(torch.randn(150, C, generator=g), dim=1)
+    d2 = torch.nn.functional.normalize(torch.randn(170, C, generator=g), dim=1)
+    q, t, _ = O.mnn_match(d1.numpy(), d2.numpy())
+    m = X.get_matches(d1.to("cuda"), d2.to("cuda"), "bfmatcher", crossCheck=True)      # use_tensor_cores defaults to True
+    assert [(a.queryIdx, a.trainIdx) for a in m] == list(zip(q.tolist(), t.tolist()))

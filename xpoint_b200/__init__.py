@@ -11,7 +11,8 @@ from .cross_scan import (CrossMergeF, CrossMergeTritonF, CrossScanF, CrossScanTr
                          merge_norm_gate)
 from .postprocess import (DMatch, NNMatcher, box_nms, detector_post, estimate_homography, find_homography, get_matches,
                           interpolate_descriptors, mnn_match, nms_keypoints, normalize_descriptors, sample_descriptors)
-from .selective_scan import (SelectiveScanCuda, selective_scan_cuda_oflex, selective_scan_fn, selective_scan_fn_mamba)
+from .selective_scan import (SelectiveScanCuda, selective_scan_cuda_oflex, selective_scan_fn, selective_scan_fn_csms6s,
+                             selective_scan_fn_mamba)
 from .vmamba import PRESETS, SS2D, VSSM, VSSBlock, build_vssm
 from .xpoint import GraphedPairPipeline, PairPipeline, PairResult, XPoint
 

@@ -194,7 +194,11 @@ extern "C" int xp_mnn_match(const float* d1, const float* d2, const int32_t* n1,
     XP_LAUNCH_CHECK("row_norm2_kernel");
     row_norm2_kernel<<<(unsigned)ceil_div(b, 8), 256, 0, st>>>(d2, ynorm, b, (int)C);
     XP_LAUNCH_CHECK("row_norm2_kernel");
-    if (use_tensor_cores) {
+    // The tensor-core kernel needs C % 32 == 0, 32 <= C <= 1024 and 16-byte-aligned descriptors (TMA boxes); any other
+    // descriptor size the reference accepts (get_matches has no such restriction, matching.py:4-36) takes the exact
+    // fp32 CUDA-core kernels instead of failing.
+    const bool tc_ok = C % 32 == 0 && C >= 32 && C <= 1024 && ((reinterpret_cast<uintptr_t>(d1) | reinterpret_cast<uintptr_t>(d2)) & 15) == 0;
+    if (use_tensor_cores && tc_ok) {
         int rc = mnn_argmin_tc(d1, d2, n1, n2, P, n1_stride, n2_stride, C, xnorm, ynorm, o12, o21, split_ws, st);
         if (rc) return rc;
     } else {

@@ -172,12 +172,23 @@ class _OflexModule:
 selective_scan_cuda_oflex = _OflexModule()
 
 
+def _out_float(oflex, backend):
+    """csms6s.py:76-85: backend None / 'oflex' honours `oflex` (fp32 output when set); 'core' and 'mamba' are the
+    extension flavours whose output dtype is the input dtype; 'torch' is the reference's CPU/torch fallback."""
+    if backend == "torch":
+        raise RuntimeError("xpoint_b200 ships only the CUDA path; backend='torch' (the reference's "
+                           "selective_scan_torch fallback) is not available")
+    if backend not in (None, "oflex", "core", "mamba"):
+        raise ValueError(f"unknown selective-scan backend {backend!r}")
+    return bool(oflex) if backend in (None, "oflex") else False
+
+
 class SelectiveScanCuda(torch.autograd.Function):
     """Same name / argument order as csms6s.py:71-87.  Forward only (inference tier)."""
 
     @staticmethod
     def forward(ctx, u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=False, oflex=True, backend=None):
-        out, _ = scan_forward(u, delta, A, B, C, D, None, delta_bias, delta_softplus, out_float=oflex)
+        out, _ = scan_forward(u, delta, A, B, C, D, None, delta_bias, delta_softplus, out_float=_out_float(oflex, backend))
         return out
 
     @staticmethod
@@ -194,8 +205,16 @@ def selective_scan_fn_mamba(u, delta, A, B, C, D=None, z=None, delta_bias=None, 
     return (out, last) if return_last_state else out
 
 
+def selective_scan_fn_csms6s(u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=True, oflex=True, backend=None):
+    """Explicit entry point with the importable reference signature (csms6s.py:112-126); no argument sniffing."""
+    return SelectiveScanCuda.apply(u, delta, A, B, C, D, delta_bias, delta_softplus, oflex, backend)
+
+
 def selective_scan_fn(u, delta, A, B, C, D=None, *args, **kwargs):
-    """Drop-in for csms6s.selective_scan_fn; also accepts the mamba_ssm-style argument list (module docstring)."""
+    """Drop-in for csms6s.selective_scan_fn; also accepts the mamba_ssm-style argument list (module docstring).
+    The two styles are told apart by what follows D: a 3-D tensor (z) / a tensor-or-None in the second slot / the
+    keywords z= or return_last_state= mean mamba style; everything else is the csms6s style.  Callers that want no
+    guessing use selective_scan_fn_csms6s / selective_scan_fn_mamba."""
     mamba_style = "z" in kwargs or "return_last_state" in kwargs
     if args:
         first = args[0]
@@ -214,12 +233,5 @@ def selective_scan_fn(u, delta, A, B, C, D=None, *args, **kwargs):
         if k not in params:
             raise TypeError(f"selective_scan_fn: unexpected keyword argument {k!r}")
         params[k] = v
-    if params["backend"] == "torch":
-        raise RuntimeError("xpoint_b200 ships only the CUDA path; backend='torch' (the reference's "
-                           "selective_scan_torch fallback) is not available")
-    if params["backend"] not in (None, "oflex", "core", "mamba"):
-        raise ValueError(f"unknown selective-scan backend {params['backend']!r}")
-    # core / mamba backends return the input dtype (csms6s.py:81-85); oflex honours the flag
-    oflex = bool(params["oflex"]) if params["backend"] in (None, "oflex") else False
-    out, _ = scan_forward(u, delta, A, B, C, D, None, params["delta_bias"], params["delta_softplus"], out_float=oflex)
-    return out
+    return SelectiveScanCuda.apply(u, delta, A, B, C, D, params["delta_bias"], params["delta_softplus"], params["oflex"],
+                                   params["backend"])

@@ -218,7 +218,9 @@ class XPoint(nn.Module):
             xf, pend = self.encoder.forward_features(data["image"])
             cdt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else torch.float32
             if pp.encoder_tail_supported(xf):
-                encoder_output, padded = pp.encoder_tail(xf, pend, 4, pad_dtype=cdt)
+                # xp_encoder_tail's padded output is ReflectionPad2d(1); with reflection_pad=False the module's own
+                # ZeroPad2d is applied inside _heads_fused instead (XPoint.py:101-104)
+                encoder_output, padded = pp.encoder_tail(xf, pend, 4, pad_dtype=cdt if self.config["reflection_pad"] else None)
             else:
                 x = self.encoder.depth_to_space((xf if pend is None else xf + pend).permute(0, 3, 1, 2), 4)
                 encoder_output, padded = x, None
@@ -280,6 +282,8 @@ class PairPipeline:
 
     def __init__(self, net: Optional[XPoint], nms=8, detection_threshold=0.015, iou=0.1, keep_top_k=4096,
                  use_tensor_cores=True, estimate_homography=False, reprojection_threshold=3.0, ransac_iters=2048):
+        if keep_top_k < 0:
+            raise ValueError("keep_top_k must be >= 0 (0 = no cap, as utils.box_nms)")
         self.net = net
         self.nms, self.thr, self.iou, self.topk = nms, detection_threshold, iou, keep_top_k
         self.use_tensor_cores = use_tensor_cores
@@ -287,18 +291,42 @@ class PairPipeline:
         # BASELINE's step ends at the matches
         self.estimate_homography, self.reproj_thr, self.ransac_iters = estimate_homography, reprojection_threshold, ransac_iters
 
-    def tail(self, prob_o, prob_t, desc_o, desc_t, channel_last=False) -> PairResult:
+    def capacity(self, H: int, W: int) -> int:
+        """Keypoint rows per image.  keep_top_k = 0 is the reference's "no cap" (utils.py:179, configs/cipdp.yaml:55):
+        the greedy NMS itself bounds the survivors -- the footprint of a kept pixel contains every pixel within
+        Chebyshev distance 4 for box side 8, in general distance d = max |dx| with (s - d)^2 above the IoU
+        bound, so kept pixels own disjoint (d+1)x(d+1) blocks."""
+        if self.topk > 0:
+            return self.topk
+        s, t = float(self.nms), float(self.iou)
+        bound = 2.0 * s * s * t / (1.0 + t)
+        d = 0
+        while (s - (d + 1)) > 0 and (s - (d + 1)) ** 2 > bound:
+            d += 1
+        blk = d + 1
+        return ((H + blk - 1) // blk + 1) * ((W + blk - 1) // blk + 1)
+
+    def tail(self, prob_o, prob_t, desc_o, desc_t, channel_last=False, valid_mask_o=None, valid_mask_t=None) -> PairResult:
         """prob (B,1,H,W) fp32; desc (B,256,Hc,Wc) fp32 [or (B,Hc,Wc,256) with channel_last] -> keypoints, descriptors
-        and mutual matches."""
+        and mutual matches.  valid_mask_* (B,1,H,W): the evaluation's `prob * data[...]['valid_mask']`
+        (evaluation.py:250-251), applied before NMS."""
+        if valid_mask_o is not None:
+            prob_o = prob_o * valid_mask_o.reshape(prob_o.shape).to(prob_o.dtype)
+        if valid_mask_t is not None:
+            prob_t = prob_t * valid_mask_t.reshape(prob_t.shape).to(prob_t.dtype)
         return self.tail_batched(torch.cat([prob_o, prob_t], 0), torch.cat([desc_o, desc_t], 0), channel_last)
 
-    def tail_batched(self, prob, desc, channel_last=False) -> PairResult:
-        """The same on the 2B batch the encoder produced (optical images first, then thermal): no concatenation."""
+    def tail_batched(self, prob, desc, channel_last=False, valid_mask=None) -> PairResult:
+        """The same on the 2B batch the encoder produced (optical images first, then thermal): no concatenation.
+        valid_mask: optional (2B,1,H,W) / (2B,H,W) multiplier applied to prob before NMS (evaluation.py:250-251)."""
         B, H, W = prob.shape[0] // 2, prob.shape[-2], prob.shape[-1]
         prob = prob.reshape(2 * B, H, W)
-        kps = pp.nms_keypoints(prob, self.nms, self.thr, self.iou, self.topk, kp_threshold=self.thr, capacity=self.topk,
+        if valid_mask is not None:
+            prob = prob * valid_mask.reshape(2 * B, H, W).to(prob.dtype)
+        cap = self.capacity(H, W)
+        kps = pp.nms_keypoints(prob, self.nms, self.thr, self.iou, self.topk, kp_threshold=self.thr, capacity=cap,
                                want_map=False)
-        count = torch.clamp(kps.count, max=self.topk)
+        count = torch.clamp(kps.count, max=cap)
         d = pp.sample_descriptors(kps.keypoints, count, desc, H, W, channel_last)
         m = pp.mnn_match(d[:B], d[B:], count[:B], count[B:], use_tensor_cores=self.use_tensor_cores)
         hom = (None, None, None)
@@ -316,11 +344,17 @@ class PairPipeline:
         return GraphedPairPipeline(self, optical, thermal, warmup)
 
     @torch.no_grad()
-    def __call__(self, optical: torch.Tensor, thermal: torch.Tensor) -> PairResult:
+    def __call__(self, optical: torch.Tensor, thermal: torch.Tensor, valid_mask_optical: Optional[torch.Tensor] = None,
+                 valid_mask_thermal: Optional[torch.Tensor] = None) -> PairResult:
         out = self.net.forward_pair_batched(optical, thermal, want_desc=False, split=False)
+        mask = None
+        if valid_mask_optical is not None or valid_mask_thermal is not None:
+            ones = torch.ones_like(optical, dtype=torch.float32)
+            mask = torch.cat([ones if valid_mask_optical is None else valid_mask_optical.reshape(optical.shape).float(),
+                              ones if valid_mask_thermal is None else valid_mask_thermal.reshape(thermal.shape).float()], 0)
         if out.get("desc_cl") is not None:
-            return self.tail_batched(out["prob"], out["desc_cl"], channel_last=True)
-        return self.tail_batched(out["prob"], out["desc"])
+            return self.tail_batched(out["prob"], out["desc_cl"], channel_last=True, valid_mask=mask)
+        return self.tail_batched(out["prob"], out["desc"], valid_mask=mask)
 
 
 class GraphedPairPipeline:

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define XP_ABI_VERSION 3
+#define XP_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define XP_API __attribute__((visibility("default")))
@@ -178,6 +178,32 @@ XP_API int xp_ss2d_dt_proj(const void* dts_r, const float* weight, void* delta, 
                            int64_t L, int64_t x_batch_stride, int64_t x_group_stride, int64_t x_rank_stride, int32_t dtype,
                            xp_stream_t stream);
 XP_API int xp_ss2d_merge_norm(const float* ys, const float* gamma, const float* beta, const void* zact, void* out,
+                              int64_t B, int64_t D, int64_t H, int64_t W, int32_t out_dtype, float eps,
+                              xp_stream_t stream);
+
+/* -- a1+a3+a4 fused (ABI 4): the SS2D core with CrossMerge inside the scan ------------------
+ * Replaces cross_scan_fn -> selective_scan_fn -> cross_merge_fn of SS2D.forward_corev2 (VMamba.py:603-632; CrossMerge
+ * csm_triton.py:56-85) for d_state 1 | 2: the four directional scans of a channel accumulate into shared-memory token
+ * planes and the MERGED y (B, D, H, W) fp32 = ys0 + flip(ys2) + (ys1 + flip(ys3))^T is written once -- no per-direction
+ * y planes in HBM.  Inputs are those of the copy-free path above, in the fused direction order:
+ *   xx (B, 2, D, L) = [x ; x^T] (xp_ss2d_dwconv_pack / xp_ss2d_pack), delta (B, 4, D, L) (xp_ss2d_dt_proj; softplus and
+ *   delta_bias are applied here), B / C (B, 4, N, L) as strided views (element strides; unit stride along L),
+ *   A (4*D, N), D (4*D) or NULL, delta_bias (4*D) or NULL, all fp32.
+ * xp_ss2d_core_channels returns how many channels of one image a CTA holds for this shape, or 0 when a token plane does
+ * not fit in shared memory (then use xp_selective_scan_fwd + xp_ss2d_merge_norm).
+ * xp_ss2d_plane_norm: y (B, D, H, W) fp32 (the output above) -> out (B, H, W, D) = LayerNorm_D(y) * gamma + beta [* zact]:
+ * out_norm (+ gate) of VMamba.py:641-646 / :369-372 reading 4 bytes per element. */
+typedef struct xp_ss2d_core_args {
+    const void* xx; const void* delta; const void* B; const void* C;
+    const float* A; const float* D; const float* delta_bias;
+    void* out;
+    int64_t batch, d_inner, dstate, H, W;
+    int64_t B_batch_stride, B_group_stride, B_state_stride, C_batch_stride, C_group_stride, C_state_stride;
+    int32_t in_dtype, delta_softplus;
+} xp_ss2d_core_args;
+XP_API int32_t xp_ss2d_core_channels(int64_t d_inner, int64_t dstate, int64_t H, int64_t W, int32_t in_dtype);
+XP_API int xp_ss2d_core(const xp_ss2d_core_args* args, xp_stream_t stream);
+XP_API int xp_ss2d_plane_norm(const float* y, const float* gamma, const float* beta, const void* zact, void* out,
                               int64_t B, int64_t D, int64_t H, int64_t W, int32_t out_dtype, float eps,
                               xp_stream_t stream);
 

@@ -305,3 +305,69 @@ def test_gelu_erf_epilogue_accuracy():
     ref = torch.nn.functional.gelu(x.half().float()[:, :64])
     assert (out - ref).abs().max() <= 1e-3 * 8 / 8 + 2 ** -11 * ref.abs().max()   # fp16 output rounding only
     np.testing.assert_allclose(out.numpy(), ref.half().float().numpy(), rtol=2e-3, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------ fused SS2D core (xp_ss2d_core)
+CORE_SHAPES = [(128, 160, 8), (64, 80, 12), (32, 40, 24), (16, 20, 36), (12, 20, 8), (8, 8, 4), (36, 44, 6), (4, 4, 2),
+               (20, 16, 5), (128, 4, 3)]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("N", [1, 2])
+@pytest.mark.parametrize("H,W,D", CORE_SHAPES)
+def test_ss2d_core_matches_scan_plus_merge(H, W, D, N, dtype):
+    """xp_ss2d_core (four directions merged in shared memory, one fp32 plane out) against the op-level path it replaces:
+    xp_selective_scan_fwd with the fused addressing (four fp32 planes in natural order) summed like CrossMerge
+    (csm_triton.py:56-85).  Covers whole and partial 256/512-token blocks, planes of 1..12 channels per CTA, multi-warp
+    step pipelining (128x160) and both column pitches."""
+    from xpoint_b200 import ss2d as S
+    from xpoint_b200.selective_scan import scan_forward
+    if S.core_channels(D, N, H, W, dtype) == 0:
+        pytest.skip("plane does not fit in shared memory for this dtype")
+    g = torch.Generator().manual_seed(H * 1000 + W * 10 + N)
+    B, K, L, R = 3, 4, H * W, 3
+    x = torch.randn(B, D, H, W, generator=g)
+    xx = torch.stack([x.reshape(B, D, L), x.transpose(2, 3).reshape(B, D, L)], 1).to(dtype).to(DEV)      # [x ; x^T]
+    delta = (0.5 * torch.rand(B, K, D, L, generator=g) - 0.3).to(dtype).to(DEV)
+    x_dbl = torch.randn(B, K, R + 2 * N, L, generator=g).to(dtype).to(DEV)
+    Bs, Cs = x_dbl[:, :, R:R + N], x_dbl[:, :, R + N:]
+    A = (-0.5 * torch.rand(K * D, N, generator=g) - 0.01).to(DEV)
+    Ds = torch.randn(K * D, generator=g).to(DEV)
+    bias = (0.5 * torch.rand(K * D, generator=g)).to(DEV)
+    ys, _ = scan_forward(xx.view(B, 2 * D, L), delta.view(B, K * D, L), A, Bs, Cs, Ds, None, bias, True, True,
+                         u_group_div=2, reverse_group_mask=S.REVERSE_MASK)
+    ys = ys.view(B, K, D, L)
+    want = (ys[:, 0] + ys[:, 1]).view(B, D, H, W) + (ys[:, 2] + ys[:, 3]).view(B, D, W, H).transpose(2, 3)
+    got = S.ss2d_core(xx, delta, A, Bs, Cs, Ds, bias, H, W, True)
+    torch.cuda.synchronize()
+    assert got.shape == (B, D, H, W) and got.dtype == torch.float32
+    assert_close(got.cpu().numpy(), want.cpu().numpy(), 2e-5, f"ss2d_core {H}x{W} D={D} N={N} {dtype}")
+    # bit-reproducible: the merge order inside the kernel does not depend on which direction reaches a block first
+    again = S.ss2d_core(xx, delta, A, Bs, Cs, Ds, bias, H, W, True)
+    assert torch.equal(got, again)
+    # out_norm on the merged plane == merge_norm on the four planes
+    gam, bet = torch.randn(D, generator=g).to(DEV), torch.randn(D, generator=g).to(DEV)
+    n1 = S.ss2d_plane_norm(got, gam, bet, None, 1e-5, out_dtype=dtype)
+    n4 = S.ss2d_merge_norm(ys, H, W, gam, bet, None, 1e-5, out_dtype=dtype)
+    assert_close(n1.float().cpu().numpy(), n4.float().cpu().numpy(), 2e-5 if dtype == torch.float32 else 1e-2, "plane_norm")
+
+
+def test_ss2d_core_no_softplus_and_optional_operands():
+    from xpoint_b200 import ss2d as S
+    from xpoint_b200.selective_scan import scan_forward
+    g = torch.Generator().manual_seed(5)
+    B, D, H, W, N, K = 2, 6, 24, 28, 1, 4
+    L = H * W
+    x = torch.randn(B, D, H, W, generator=g)
+    xx = torch.stack([x.reshape(B, D, L), x.transpose(2, 3).reshape(B, D, L)], 1).half().to(DEV)
+    delta = (0.4 * torch.rand(B, K, D, L, generator=g) + 0.01).half().to(DEV)
+    bc = torch.randn(B, K, 2 * N, L, generator=g).half().to(DEV)
+    A = (-0.5 * torch.rand(K * D, N, generator=g)).to(DEV)
+    ys, _ = scan_forward(xx.view(B, 2 * D, L), delta.view(B, K * D, L), A, bc[:, :, :N], bc[:, :, N:], None, None, None, False,
+                         True, u_group_div=2, reverse_group_mask=S.REVERSE_MASK)
+    ys = ys.view(B, K, D, L)
+    want = (ys[:, 0] + ys[:, 1]).view(B, D, H, W) + (ys[:, 2] + ys[:, 3]).view(B, D, W, H).transpose(2, 3)
+    got = S.ss2d_core(xx, delta, A, bc[:, :, :N], bc[:, :, N:], None, None, H, W, False)
+    assert_close(got.cpu().numpy(), want.cpu().numpy(), 2e-5, "ss2d_core without softplus / D / bias")
+    with pytest.raises(RuntimeError):
+        S.ss2d_core(xx, delta, A, bc[:, :, :N], bc[:, :, N:], None, None, H, W + 4, False)

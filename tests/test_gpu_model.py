@@ -254,3 +254,24 @@ def test_pipeline_topk_zero_means_no_cap():
         assert int(r.n_matches[0]) > 0
     with pytest.raises(ValueError):
         X.PairPipeline(None, keep_top_k=-1)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_ss2d_fused_core_matches_default_path(dtype):
+    """SS2D with the fused core (xp_ss2d_core + xp_ss2d_plane_norm, `use_core`) against the default copy-free path
+    (xp_selective_scan_fwd + xp_ss2d_merge_norm) and the CrossScan/CrossMerge kernels, at two stage shapes."""
+    import xpoint_b200 as X
+    for C, H, W, N, ft in ((96, 64, 80, 1, "v05_noz"), (48, 32, 40, 2, "v05")):
+        torch.manual_seed(0)
+        m = X.SS2D(d_model=C, d_state=N, ssm_ratio=1.0, forward_type=ft, conv_bias=False).to(DEV).eval()
+        x = torch.randn(2, H, W, C, device=DEV)
+        with torch.no_grad(), torch.autocast("cuda", dtype=dtype, enabled=dtype != torch.float32):
+            y0 = m(x)
+            m.use_core = True
+            y1 = m(x)
+            m.use_core = False
+            m.disable_fused = True
+            y2 = m(x)
+        tol = 2e-5 if dtype == torch.float32 else 1e-2
+        assert_close(y1.float().cpu().numpy(), y0.float().cpu().numpy(), tol, f"fused core vs default C={C} {dtype}")
+        assert_close(y1.float().cpu().numpy(), y2.float().cpu().numpy(), tol, f"fused core vs CrossScan path C={C} {dtype}")

@@ -36,6 +36,16 @@ class ScanArgs(Structure):
     )
 
 
+class CoreArgs(Structure):
+    """Mirror of xp_ss2d_core_args (include/xpoint_b200.h)."""
+    _fields_ = (
+        [(n, c_void_p) for n in ("xx", "delta", "B", "C", "A", "D", "delta_bias", "out")]
+        + [(n, c_int64) for n in ("batch", "d_inner", "dstate", "H", "W", "B_batch_stride", "B_group_stride", "B_state_stride",
+                                  "C_batch_stride", "C_group_stride", "C_state_stride")]
+        + [(n, c_int32) for n in ("in_dtype", "delta_softplus")]
+    )
+
+
 _SIGNATURES = {
     "xp_abi_version": (ctypes.c_int, []),
     "xp_last_error": (c_char_p, []),
@@ -51,6 +61,9 @@ _SIGNATURES = {
     "xp_ss2d_dwconv_pack": (ctypes.c_int, [c_void_p] * 4 + [c_int64] * 5 + [c_int32, c_int32, c_void_p]),
     "xp_ss2d_dt_proj": (ctypes.c_int, [c_void_p] * 3 + [c_int64] * 8 + [c_int32, c_void_p]),
     "xp_ss2d_merge_norm": (ctypes.c_int, [c_void_p] * 5 + [c_int64] * 4 + [c_int32, c_float, c_void_p]),
+    "xp_ss2d_core_channels": (c_int32, [c_int64] * 4 + [c_int32]),
+    "xp_ss2d_core": (ctypes.c_int, [POINTER(CoreArgs), c_void_p]),
+    "xp_ss2d_plane_norm": (ctypes.c_int, [c_void_p] * 5 + [c_int64] * 4 + [c_int32, c_float, c_void_p]),
     "xp_layer_norm": (ctypes.c_int, [c_void_p] * 4 + [c_int64, c_int64, c_int32, c_int32, c_float, c_void_p]),
     "xp_add_layer_norm": (ctypes.c_int, [c_void_p] * 7 + [c_int64, c_int64] + [c_int32] * 4 + [c_float, c_void_p]),
     "xp_patch_embed_stem": (ctypes.c_int, [c_void_p] * 6 + [c_int64] * 5 + [c_float, c_int32, c_int32, c_void_p]),
@@ -102,7 +115,7 @@ def lib() -> ctypes.CDLL:
             fn = getattr(handle, name)  # raises AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if handle.xp_abi_version() != 3:
+        if handle.xp_abi_version() != 4:
             raise RuntimeError("libxpoint_b200.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -234,7 +234,7 @@ template <typename TO, int TH, int TW, int DPER>
 __global__ void __launch_bounds__(256) ss2d_merge_norm_kernel(const float* __restrict__ ys, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, const TO* __restrict__ zact,
                                                               TO* __restrict__ out, int D, int H, int W, int tiles_w,
-                                                              int tiles_h, float eps) {
+                                                              int tiles_h, float eps, int planes) {
     extern __shared__ __align__(16) float tile[];
     const int P = D | 1;                                   // odd pitch: conflict-free token-major writes
     const int L = H * W;                                   // D * L < 2^31 (host-checked): 32-bit offsets inside a plane set
@@ -244,7 +244,9 @@ __global__ void __launch_bounds__(256) ss2d_merge_norm_kernel(const float* __res
     const int64_t b = t;
     const int h0 = th * TH, w0 = tw * TW;
     const int tid = threadIdx.x;
-    const float* y0 = ys + (b * 4 + 0) * D * (int64_t)L;
+    // planes == 1: ys is the already merged (B, D, H, W) plane of xp_ss2d_core -- phase 1 copies it, phase 2 is skipped
+    const bool merged = planes == 1;
+    const float* y0 = ys + (b * planes + 0) * D * (int64_t)L;
     const float* y1 = y0 + (int64_t)D * L;
     const float* y2 = y1 + (int64_t)D * L;
     const float* y3 = y2 + (int64_t)D * L;
@@ -261,8 +263,12 @@ __global__ void __launch_bounds__(256) ss2d_merge_norm_kernel(const float* __res
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (ok) {
                 const float4 a = __ldg(reinterpret_cast<const float4*>(y0 + c * L + base));
-                const float4 r = __ldg(reinterpret_cast<const float4*>(y1 + c * L + base));
-                v = make_float4(a.x + r.x, a.y + r.y, a.z + r.z, a.w + r.w);
+                if (merged) {
+                    v = a;
+                } else {
+                    const float4 r = __ldg(reinterpret_cast<const float4*>(y1 + c * L + base));
+                    v = make_float4(a.x + r.x, a.y + r.y, a.z + r.z, a.w + r.w);
+                }
             }
             dst[c] = v.x; dst[P + c] = v.y; dst[2 * P + c] = v.z; dst[3 * P + c] = v.w;
         }
@@ -275,7 +281,7 @@ __global__ void __launch_bounds__(256) ss2d_merge_norm_kernel(const float* __res
         const bool ok = h < H && w < W;
         const int base = w * H + h;
         float* dst = tile + ((4 * q) * TW + ww) * P;
-        if (ok) {
+        if (ok && !merged) {
 #pragma unroll 4
             for (int c = tid / (QH * TW); c < D; c += cstep) {
                 const float4 a = __ldg(reinterpret_cast<const float4*>(y2 + c * L + base));
@@ -465,39 +471,39 @@ __global__ void __launch_bounds__(256) ss2d_dt_proj16_kernel(const T* __restrict
 
 template <typename TO, int TH, int TW, int DPER>
 static int merge_norm_launch_d(const float* ys, const float* gamma, const float* beta, const void* zact, void* out, int64_t B,
-                               int64_t D, int64_t H, int64_t W, float eps, cudaStream_t st) {
+                               int64_t D, int64_t H, int64_t W, float eps, cudaStream_t st, int planes) {
     const int tiles_w = (int)ceil_div(W, TW), tiles_h = (int)ceil_div(H, TH);
     const int smem = TH * TW * (int)(D | 1) * 4;
     auto kern = ss2d_merge_norm_kernel<TO, TH, TW, DPER>;
     XP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kern<<<(unsigned)(B * tiles_h * tiles_w), 256, smem, st>>>(ys, gamma, beta, (const TO*)zact, (TO*)out, (int)D, (int)H, (int)W,
-                                                                 tiles_w, tiles_h, eps);
+                                                                 tiles_w, tiles_h, eps, planes);
     XP_LAUNCH_CHECK("ss2d_merge_norm_kernel");
     return XP_OK;
 }
 
 template <typename TO, int TH, int TW>
 static int merge_norm_launch(const float* ys, const float* gamma, const float* beta, const void* zact, void* out, int64_t B,
-                             int64_t D, int64_t H, int64_t W, float eps, cudaStream_t st) {
+                             int64_t D, int64_t H, int64_t W, float eps, cudaStream_t st, int planes) {
     const int per = (int)ceil_div(D, 32);                  // channels per lane in the LayerNorm phase
-    if (per <= 3) return merge_norm_launch_d<TO, TH, TW, 3>(ys, gamma, beta, zact, out, B, D, H, W, eps, st);
-    if (per <= 6) return merge_norm_launch_d<TO, TH, TW, 6>(ys, gamma, beta, zact, out, B, D, H, W, eps, st);
-    if (per <= 12) return merge_norm_launch_d<TO, TH, TW, 12>(ys, gamma, beta, zact, out, B, D, H, W, eps, st);
-    if (per <= 24) return merge_norm_launch_d<TO, TH, TW, 24>(ys, gamma, beta, zact, out, B, D, H, W, eps, st);
-    return merge_norm_launch_d<TO, TH, TW, 0>(ys, gamma, beta, zact, out, B, D, H, W, eps, st);
+    if (per <= 3) return merge_norm_launch_d<TO, TH, TW, 3>(ys, gamma, beta, zact, out, B, D, H, W, eps, st, planes);
+    if (per <= 6) return merge_norm_launch_d<TO, TH, TW, 6>(ys, gamma, beta, zact, out, B, D, H, W, eps, st, planes);
+    if (per <= 12) return merge_norm_launch_d<TO, TH, TW, 12>(ys, gamma, beta, zact, out, B, D, H, W, eps, st, planes);
+    if (per <= 24) return merge_norm_launch_d<TO, TH, TW, 24>(ys, gamma, beta, zact, out, B, D, H, W, eps, st, planes);
+    return merge_norm_launch_d<TO, TH, TW, 0>(ys, gamma, beta, zact, out, B, D, H, W, eps, st, planes);
 }
 
 template <typename TO>
 static int merge_norm_dispatch(const float* ys, const float* gamma, const float* beta, const void* zact, void* out, int64_t B,
-                               int64_t D, int64_t H, int64_t W, float eps, cudaStream_t st) {
+                               int64_t D, int64_t H, int64_t W, float eps, cudaStream_t st, int planes) {
     // 8x8 tokens for narrow blocks (25 KiB tile, 8 CTAs / SM at D = 96); from D = 192 on the 4x8 tile wins because it
     // doubles the resident CTAs (measured on B200: D = 192 1.01 -> 0.58 ms, D = 768 0.26 -> 0.18 ms); 4x4 for very wide blocks
     static const int tile_env = getenv("XP_MN_TILE") ? atoi(getenv("XP_MN_TILE")) : 0;     // tuning knob: 48 = 4x8, 44 = 4x4
-    if (tile_env == 48 && D <= 1536) return merge_norm_launch<TO, 4, 8>(ys, gamma, beta, zact, out, B, D, H, W, eps, st);
-    if (tile_env == 44) return merge_norm_launch<TO, 4, 4>(ys, gamma, beta, zact, out, B, D, H, W, eps, st);
-    if (D <= 128) return merge_norm_launch<TO, 8, 8>(ys, gamma, beta, zact, out, B, D, H, W, eps, st);
-    if (D <= 1536) return merge_norm_launch<TO, 4, 8>(ys, gamma, beta, zact, out, B, D, H, W, eps, st);
-    return merge_norm_launch<TO, 4, 4>(ys, gamma, beta, zact, out, B, D, H, W, eps, st);
+    if (tile_env == 48 && D <= 1536) return merge_norm_launch<TO, 4, 8>(ys, gamma, beta, zact, out, B, D, H, W, eps, st, planes);
+    if (tile_env == 44) return merge_norm_launch<TO, 4, 4>(ys, gamma, beta, zact, out, B, D, H, W, eps, st, planes);
+    if (D <= 128) return merge_norm_launch<TO, 8, 8>(ys, gamma, beta, zact, out, B, D, H, W, eps, st, planes);
+    if (D <= 1536) return merge_norm_launch<TO, 4, 8>(ys, gamma, beta, zact, out, B, D, H, W, eps, st, planes);
+    return merge_norm_launch<TO, 4, 4>(ys, gamma, beta, zact, out, B, D, H, W, eps, st, planes);
 }
 
 }  // namespace xp
@@ -546,24 +552,35 @@ extern "C" int xp_ss2d_dwconv_pack(const void* in, const float* weight, const fl
     return XP_OK;
 }
 
-extern "C" int xp_ss2d_merge_norm(const float* ys, const float* gamma, const float* beta, const void* zact, void* out,
-                                  int64_t B, int64_t D, int64_t H, int64_t W, int32_t out_dtype, float eps,
-                                  xp_stream_t stream) {
-    XP_REQUIRE(ys && gamma && beta && out, "xp_ss2d_merge_norm: NULL tensor pointer");
-    XP_REQUIRE(B >= 0 && D > 0 && H > 0 && W > 0, "xp_ss2d_merge_norm: bad shape");
-    XP_REQUIRE(H % 4 == 0 && W % 4 == 0, "xp_ss2d_merge_norm: H and W must be multiples of 4 (got %lld x %lld)", (long long)H,
-               (long long)W);
-    XP_REQUIRE(D <= 3072, "xp_ss2d_merge_norm: D must be <= 3072 (got %lld)", (long long)D);
-    XP_REQUIRE(D * H * W < ((int64_t)1 << 31), "xp_ss2d_merge_norm: D*H*W must be < 2^31");
-    XP_REQUIRE(out_dtype >= XP_F32 && out_dtype <= XP_BF16, "xp_ss2d_merge_norm: unsupported dtype %d", out_dtype);
-    XP_REQUIRE((reinterpret_cast<uintptr_t>(ys) & 15) == 0, "xp_ss2d_merge_norm: ys must be 16-byte aligned");
+static int merge_norm_entry(const char* who, const float* ys, const float* gamma, const float* beta, const void* zact, void* out,
+                            int64_t B, int64_t D, int64_t H, int64_t W, int32_t out_dtype, float eps, xp_stream_t stream,
+                            int planes) {
+    XP_REQUIRE(ys && gamma && beta && out, "%s: NULL tensor pointer", who);
+    XP_REQUIRE(B >= 0 && D > 0 && H > 0 && W > 0, "%s: bad shape", who);
+    XP_REQUIRE(H % 4 == 0 && W % 4 == 0, "%s: H and W must be multiples of 4 (got %lld x %lld)", who, (long long)H, (long long)W);
+    XP_REQUIRE(D <= 3072, "%s: D must be <= 3072 (got %lld)", who, (long long)D);
+    XP_REQUIRE(D * H * W < ((int64_t)1 << 31), "%s: D*H*W must be < 2^31", who);
+    XP_REQUIRE(out_dtype >= XP_F32 && out_dtype <= XP_BF16, "%s: unsupported dtype %d", who, out_dtype);
+    XP_REQUIRE((reinterpret_cast<uintptr_t>(ys) & 15) == 0, "%s: the y planes must be 16-byte aligned", who);
     if (B == 0) return XP_OK;
     cudaStream_t st = (cudaStream_t)stream;
     switch (out_dtype) {
-        case XP_F32: return merge_norm_dispatch<float>(ys, gamma, beta, zact, out, B, D, H, W, eps, st);
-        case XP_F16: return merge_norm_dispatch<__half>(ys, gamma, beta, zact, out, B, D, H, W, eps, st);
-        default: return merge_norm_dispatch<__nv_bfloat16>(ys, gamma, beta, zact, out, B, D, H, W, eps, st);
+        case XP_F32: return merge_norm_dispatch<float>(ys, gamma, beta, zact, out, B, D, H, W, eps, st, planes);
+        case XP_F16: return merge_norm_dispatch<__half>(ys, gamma, beta, zact, out, B, D, H, W, eps, st, planes);
+        default: return merge_norm_dispatch<__nv_bfloat16>(ys, gamma, beta, zact, out, B, D, H, W, eps, st, planes);
     }
+}
+
+extern "C" int xp_ss2d_merge_norm(const float* ys, const float* gamma, const float* beta, const void* zact, void* out,
+                                  int64_t B, int64_t D, int64_t H, int64_t W, int32_t out_dtype, float eps,
+                                  xp_stream_t stream) {
+    return merge_norm_entry("xp_ss2d_merge_norm", ys, gamma, beta, zact, out, B, D, H, W, out_dtype, eps, stream, 4);
+}
+
+extern "C" int xp_ss2d_plane_norm(const float* y, const float* gamma, const float* beta, const void* zact, void* out,
+                                  int64_t B, int64_t D, int64_t H, int64_t W, int32_t out_dtype, float eps,
+                                  xp_stream_t stream) {
+    return merge_norm_entry("xp_ss2d_plane_norm", y, gamma, beta, zact, out, B, D, H, W, out_dtype, eps, stream, 1);
 }
 
 extern "C" int xp_ss2d_dt_proj(const void* dts_r, const float* weight, void* delta, int64_t B, int64_t G, int64_t D, int64_t R,

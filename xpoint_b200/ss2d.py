@@ -11,6 +11,9 @@ column forward, column backward] in the reference's numbering k (csm_triton.py:2
 """
 from __future__ import annotations
 
+import ctypes
+import functools
+
 import torch
 
 from . import _lib
@@ -70,6 +73,70 @@ def ss2d_merge_norm(ys: torch.Tensor, H: int, W: int, weight: torch.Tensor, bias
             _lib.check(_lib.lib().xp_ss2d_merge_norm(_lib.ptr(ys), _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(zact),
                                                      _lib.ptr(out), B, D, H, W, _lib.dtype_code(out), float(eps),
                                                      _lib.stream_ptr(dev)))
+        _lib.count_launches(1)
+    return out
+
+
+@functools.lru_cache(maxsize=None)
+def core_channels(D: int, d_state: int, H: int, W: int, dtype: torch.dtype) -> int:
+    """Channels of one image a CTA of the fused core (xp_ss2d_core) holds for this shape; 0 = the token planes do not fit
+    in shared memory (the caller then scans with xp_selective_scan_fwd and merges with xp_ss2d_merge_norm)."""
+    if d_state > 2 or H % 4 or W % 4 or (H * W) % (4 if dtype == torch.float32 else 8):
+        return 0
+    return int(_lib.lib().xp_ss2d_core_channels(D, d_state, H, W, _lib._DTYPES[dtype]))
+
+
+def ss2d_core(xx: torch.Tensor, delta: torch.Tensor, A: torch.Tensor, Bs: torch.Tensor, Cs: torch.Tensor, Ds, delta_bias,
+              H: int, W: int, delta_softplus: bool = True) -> torch.Tensor:
+    """CrossScan -> selective scan -> CrossMerge in one kernel (VMamba.py:603-632): xx (B, 2, D, L) = [x ; x^T],
+    delta (B, 4, D, L), Bs / Cs (B, 4, N, L) strided views (unit stride along L), A (4*D, N), Ds / delta_bias (4*D) fp32,
+    all in FUSED_ORDER -> merged y (B, D, H, W) fp32."""
+    dev = _lib.require_cuda(xx, delta, A, Bs, Cs, Ds, delta_bias)
+    B, two, D, L = xx.shape
+    N = Bs.shape[2]
+    if two != 2 or L != H * W or tuple(delta.shape) != (B, 4, D, L) or tuple(Bs.shape) != (B, 4, N, L) or Cs.shape != Bs.shape:
+        raise RuntimeError("ss2d_core: expected xx (B, 2, D, L), delta (B, 4, D, L), Bs / Cs (B, 4, N, L)")
+    if not (xx.dtype == delta.dtype == Bs.dtype == Cs.dtype):
+        raise RuntimeError("ss2d_core: xx, delta, Bs, Cs must share one dtype")
+    if Bs.stride(3) != 1 or Cs.stride(3) != 1:
+        raise RuntimeError("ss2d_core: Bs / Cs need unit stride along the sequence")
+    if tuple(A.shape) != (4 * D, N) or A.dtype != torch.float32:
+        raise RuntimeError("ss2d_core: A must be fp32 of shape (4*D, N)")
+    xx, delta, A = xx.contiguous(), delta.contiguous(), A.contiguous()
+    Ds = None if Ds is None else Ds.float().contiguous()
+    delta_bias = None if delta_bias is None else delta_bias.float().contiguous()
+    out = torch.empty((B, D, H, W), dtype=torch.float32, device=dev)
+    if out.numel():
+        a = _lib.CoreArgs()
+        a.xx, a.delta, a.B, a.C = _lib.ptr(xx), _lib.ptr(delta), _lib.ptr(Bs), _lib.ptr(Cs)
+        a.A, a.D, a.delta_bias, a.out = _lib.ptr(A), _lib.ptr(Ds), _lib.ptr(delta_bias), _lib.ptr(out)
+        a.batch, a.d_inner, a.dstate, a.H, a.W = B, D, N, H, W
+        a.B_batch_stride, a.B_group_stride, a.B_state_stride = Bs.stride(0), Bs.stride(1), Bs.stride(2)
+        a.C_batch_stride, a.C_group_stride, a.C_state_stride = Cs.stride(0), Cs.stride(1), Cs.stride(2)
+        a.in_dtype, a.delta_softplus = _lib.dtype_code(xx), int(bool(delta_softplus))
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().xp_ss2d_core(ctypes.byref(a), _lib.stream_ptr(dev)))
+        _lib.count_launches(1)
+    return out
+
+
+def ss2d_plane_norm(y: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, zact=None, eps=1e-5, out_dtype=None) -> torch.Tensor:
+    """y (B, D, H, W) fp32 merged plane (ss2d_core) -> (B, H, W, D) = LayerNorm_D(y) [* zact]  (VMamba.py:641-646)."""
+    dev = _lib.require_cuda(y, weight, bias, zact)
+    if y.dim() != 4 or y.dtype != torch.float32:
+        raise RuntimeError("ss2d_plane_norm expects an fp32 (B, D, H, W) plane")
+    y = y.contiguous()
+    B, D, H, W = y.shape
+    out_dtype = out_dtype or (zact.dtype if zact is not None else y.dtype)
+    out = torch.empty((B, H, W, D), dtype=out_dtype, device=dev)
+    if zact is not None:
+        zact = zact.contiguous()
+        if zact.dtype != out_dtype or zact.numel() != out.numel():
+            raise RuntimeError("zact must match the output dtype and shape (B, H, W, D)")
+    if out.numel():
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().xp_ss2d_plane_norm(_lib.ptr(y), _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(zact), _lib.ptr(out),
+                                                     B, D, H, W, _lib.dtype_code(out), float(eps), _lib.stream_ptr(dev)))
         _lib.count_launches(1)
     return out
 

@@ -263,6 +263,11 @@ class SS2D(nn.Module):
             dts = _ss2d.ss2d_dt_proj(x_dbl[:, :, :R], w["wdt32"])                  # (B, 4, D, L), store-bound kernel
         else:
             dts = torch.matmul(w["wdt"], x_dbl.view(B, 2, 2, R + 2 * N, L)[:, :, :, :R])   # (B, 2, 2, D, L)
+        if getattr(self, "use_core", USE_CORE) and _ss2d.core_channels(D, N, H, W, xx.dtype) > 0:
+            # the four directions meet in shared memory: ONE merged fp32 plane instead of four (xp_ss2d_core)
+            y = _ss2d.ss2d_core(xx, dts.view(B, K, D, L), w["A"], x_dbl[:, :, R:R + N], x_dbl[:, :, R + N:], w["Ds"],
+                                w["dt_bias"], H, W, True)
+            return _ss2d.ss2d_plane_norm(y, w["norm_w"], w["norm_b"], zact, self.out_norm.eps, out_dtype=out_dtype or xx.dtype)
         ys, _ = scan_forward(xx.view(B, 2 * D, L), dts.view(B, K * D, L), w["A"], x_dbl[:, :, R:R + N], x_dbl[:, :, R + N:],
                              w["Ds"], None, w["dt_bias"], True, True, u_group_div=2,
                              reverse_group_mask=_ss2d.REVERSE_MASK)               # (B, 4*D, L) fp32, natural order
@@ -313,6 +318,12 @@ class SS2D(nn.Module):
 # buys 0.3 ms per stage-0 block against dt_proj + scan while the kernel's bytes/s falls.
 # XP_FUSE_DT_PROJ=1 or `module.fuse_dt_proj = True` turns it on.
 FUSE_DT_PROJ = os.environ.get("XP_FUSE_DT_PROJ", "0") not in ("", "0")
+# XP_SS2D_CORE=1 (or `module.use_core = True`): the fused core xp_ss2d_core (CrossMerge inside the scan: one merged fp32 plane
+# in HBM instead of four, 2.3x less DRAM traffic for scan + merge) replaces xp_selective_scan_fwd + xp_ss2d_merge_norm.  Built,
+# parity-tested and measured, but NOT the default: on B200 it is bound by instruction issue (12 warps / SM, 160 registers, one
+# (b, channel) plane set per SM) and runs 2.4 ms per stage-0 block against 1.5 ms for the op-level scan, which the cheaper
+# out_norm pass (0.7 vs 1.0 ms) does not win back.
+USE_CORE = os.environ.get("XP_SS2D_CORE", "0") not in ("", "0")
 
 
 class VSSBlock(nn.Module):  # VMamba.py:1153-1240

@@ -15,8 +15,13 @@ One JSON line is printed by rank 0:
   e2e        pairs/s through the public API (PairPipeline) from pinned HOST images, H2D + D2H inside the region
   roofline   selective-scan launches inside the timed region: algorithmic bytes / CUDA-event time vs measured HBM peak
   scan_microbench  BASELINE configs[1] (B=32, K*D=768, N=16, L=20480; fp32 and bf16) and the XPoint-actual N=1 shape
-  cpu_baseline     the oracle port of the same path on the host cores, 1 pair (N=1 only)
---impl reference times that CPU path as the reference arm (rank 0 only).
+  cpu_baseline     the reference's own CPU path on the host cores on a bounded sample (kind "reference": the UNMODIFIED
+                   reference staged by oracle/build_ref.py -- XPoint.forward + box_nms(on_cpu) + interpolate_descriptors +
+                   cv2 BFMatcher; kind "port": the oracle restatement when the reference is not staged), N=1 only; the GPU
+                   tail is checked bit-exactly against that run's keypoints / matches (parity_check)
+  ss2d_core        SURVEY 8d secondary figure: one stage-0 SS2D core (dwconv_pack .. out_norm) against its 1.17 GB
+  other_configs    BASELINE configs[4] (1024x1280, top-16384), preset V, single-pair latency (benchmark.py:151-164)
+--impl reference times the CPU path as the reference arm (rank 0 only; one pair per step).
 """
 import argparse
 import json
@@ -48,6 +53,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fp32-match", action="store_true", help="use the exact CUDA-core matcher instead of tcgen05")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--ref-port", action="store_true", help="CPU arm: time the oracle port even when the reference is staged")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other_configs / ss2d_core measurements")
     return ap.parse_args()
 
 
@@ -98,7 +105,7 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------ CPU arm
 def cpu_pair_run(args, n_pairs=1, threads=None):
-    """The oracle port of the whole path (oracle/model.py + oracle/xp_oracle.c) on the host cores."""
+    """kind "port": the oracle restatement of the whole path (oracle/model.py + oracle/xp_oracle.c) on the host cores."""
     import torch
     from oracle import model as M
     from oracle import oracle as O
@@ -123,13 +130,68 @@ def cpu_pair_run(args, n_pairs=1, threads=None):
     return step, threads
 
 
+def reference_staged():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import refstage
+    return refstage if refstage.available(need_ext=False) else None
+
+
+def cpu_reference_run(args, n_pairs=1, threads=None):
+    """kind "reference": the UNMODIFIED reference (baseline/_ref, staged by oracle/build_ref.py) on the host cores, driven
+    like its evaluation loop (xpoint/utils/evaluation.py:229-301 with configs/cipdp.yaml: nms 8, detection_threshold 0.015,
+    cpu_nms true): XPoint.forward (fp32, selective_scan_torch -- csms6s.py:25-68 -- because no CUDA extension is imported
+    in this process before the package) -> box_nms(on_cpu=True, keep_top_k) -> nonzero -> interpolate_descriptors ->
+    get_matches('bfmatcher', crossCheck=True).  The one patch is SURVEY 0.8's CPU CrossScan rebind."""
+    import torch
+    R = reference_staged()
+    ns = R.load(with_ext=False)
+    assert not ns.RS.WITH_SELECTIVESCAN_OFLEX, "the CPU arm must run the reference's torch path"
+    R.patch_cross_torch_path(ns)
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    net = R.build_xpoint(ns, args.preset, mixed_precision=False, height=args.height, width=args.width, seed=0)
+    g = torch.Generator().manual_seed(0)
+    opt = torch.rand(n_pairs, 1, args.height, args.width, generator=g)
+    thr = torch.rand(n_pairs, 1, args.height, args.width, generator=g)
+    U = ns.utils
+
+    def step():
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            po, pt, _ = net({"optical": {"image": opt}, "thermal": {"image": thr}})
+        nms_o = U.box_nms(po["prob"], 8, 0.015, keep_top_k=args.topk, on_cpu=True)
+        nms_t = U.box_nms(pt["prob"], 8, 0.015, keep_top_k=args.topk, on_cpu=True)
+        out = []
+        for b in range(n_pairs):
+            kp_o = torch.nonzero(nms_o[b].squeeze() > 0.015)
+            kp_t = torch.nonzero(nms_t[b].squeeze() > 0.015)
+            d_o = U.interpolate_descriptors(kp_o, po["desc"][b], args.height, args.width).numpy()
+            d_t = U.interpolate_descriptors(kp_t, pt["desc"][b], args.height, args.width).numpy()
+            m = U.get_matches(d_o, d_t, "bfmatcher", False, crossCheck=True) if len(kp_o) and len(kp_t) else []
+            out.append(dict(kp_o=kp_o, kp_t=kp_t, pairs=[(x.queryIdx, x.trainIdx) for x in m], d_o=d_o, d_t=d_t))
+        dt = time.perf_counter() - t0
+        return dt, dict(prob_o=po["prob"], prob_t=pt["prob"], desc_o=po["desc"], desc_t=pt["desc"], tail=out,
+                        state_dict=net.state_dict())
+    return step, threads
+
+
+def cpu_arm(args, n_pairs):
+    """(step, threads, kind, description) of the CPU baseline: the staged reference when present, else the oracle port."""
+    if reference_staged() is not None and not args.ref_port:
+        step, threads = cpu_reference_run(args, n_pairs)
+        return step, threads, "reference", ("unmodified reference (baseline/_ref): XPoint.forward fp32 via selective_scan_torch + "
+                                            "box_nms(on_cpu) + interpolate_descriptors + cv2.BFMatcher(crossCheck)")
+    step, threads = cpu_pair_run(args, n_pairs)
+    return step, threads, "port", "oracle/model.py + xp_oracle.c (torch CPU for dense layers): the reference is not staged here"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    NP = 8                                   # pairs per step: a bounded sample (~5 s of host work per step)
-    step, threads = cpu_pair_run(args, NP)
-    for _ in range(min(args.warmup, 1)):
+    NP = 1 if (reference_staged() is not None and not args.ref_port) else 8      # pairs per step: a bounded sample
+    step, threads, kind, what = cpu_arm(args, NP)
+    for _ in range(args.warmup):
         step()
     times = [step()[0] for _ in range(args.steps)]
     per = sum(times) / len(times)
@@ -138,9 +200,9 @@ def run_reference(args):
             "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "reference",
             "config": {"workload": f"XPoint preset {args.preset} pair inference {args.height}x{args.width}, top-{args.topk} keypoints, "
-                                   "MNN matching; CPU oracle port of the reference path", "pairs_per_step": NP},
-            "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
-                             "sample": f"{NP} pairs per step x {args.steps} steps (oracle/model.py + xp_oracle.c, torch CPU for dense layers)"},
+                                   f"MNN matching on the host cores; {what}", "pairs_per_step": NP},
+            "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": kind,
+                             "sample": f"{NP} pair(s) per step x {args.steps} steps; {what}"},
             "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -153,6 +215,15 @@ def scan_microbench(peak):
     from xpoint_b200.selective_scan import algorithmic_bytes
     out = []
     dev = "cuda"
+    # the reference's own CUDA kernel (selective_scan_cuda_oflex.fwd) compiled for sm_100a by oracle/build_ref.py, when staged:
+    # "the kernel to beat on the same box" (SURVEY 8c); timed on the same tensors, never on the product path
+    ref_ext = None
+    try:
+        R = reference_staged()
+        if R is not None and R.ext_path():
+            ref_ext = R.load_ext()
+    except Exception:
+        ref_ext = None
     cases = [("config2 fp32->fp32 N=16", 32, 768, 4, 16, 20480, torch.float32, True),
              ("config2 bf16->fp32 N=16", 32, 768, 4, 16, 20480, torch.bfloat16, True),
              ("config2 bf16->bf16 N=16", 32, 768, 4, 16, 20480, torch.bfloat16, False),
@@ -179,11 +250,207 @@ def scan_microbench(peak):
         ms = e0.elapsed_time(e1) / 100
         nbytes = algorithmic_bytes(Bt, KD, K, N, L, u.element_size(), y.element_size())
         gbs = nbytes / ms / 1e6
-        out.append({"case": name, "ms": round(ms, 4), "algorithmic_GB": round(nbytes / 1e9, 3), "achieved_GBs": round(gbs, 1),
-                    "frac_of_hbm_peak": round(gbs / peak, 4)})
+        row = {"case": name, "ms": round(ms, 4), "algorithmic_GB": round(nbytes / 1e9, 3), "achieved_GBs": round(gbs, 1),
+               "frac_of_hbm_peak": round(gbs / peak, 4)}
+        if ref_ext is not None:
+            for _ in range(5):
+                ref_ext.fwd(u, dl, A, Bm, Cm, D, bias, True, 1, oflex)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(20):
+                ref_ext.fwd(u, dl, A, Bm, Cm, D, bias, True, 1, oflex)
+            e1.record()
+            torch.cuda.synchronize()
+            ref_ms = e0.elapsed_time(e1) / 20
+            row["ref_kernel_ms"] = round(ref_ms, 4)
+            row["ref_frac_of_hbm_peak"] = round(nbytes / ref_ms / 1e6 / peak, 4)
+            row["speedup_vs_ref_kernel"] = round(ref_ms / ms, 2)
+        out.append(row)
         del u, dl, Bm, Cm, y
         torch.cuda.empty_cache()
     return out
+
+
+def ss2d_core_figure(peak, B=128):
+    """SURVEY 8d secondary figure: ONE stage-0 SS2D core of preset E (x after in_proj -> y before out_proj: depth-wise conv +
+    SiLU + CrossScan -> x_proj / dt_proj -> selective scan -> CrossMerge -> out_norm) at B images of 128x160 tokens, fp16.
+    Algorithmic bytes B*L*[(D + K(R+2N)) s_in + D s_out] = 448 B per token; times are CUDA events around each kernel."""
+    import torch
+    import xpoint_b200 as X
+    from xpoint_b200 import ss2d as S
+    from xpoint_b200.selective_scan import scan_forward
+    H, W, C = 128, 160, 96
+    L = H * W
+    torch.manual_seed(0)
+    m = X.SS2D(d_model=C, d_state=1, ssm_ratio=1.0, forward_type="v05_noz", conv_bias=False).cuda().eval().half()
+    D, K, N, R = m.d_inner, 4, 1, m.dt_rank
+    x = torch.randn(B, H, W, D, device="cuda", dtype=torch.float16)
+    w = m._fused_weights(B, torch.float16)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    times = {}
+
+    def timed(name, fn, n=10):
+        for _ in range(3):
+            r = fn()
+        a, b = ev(), ev()
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(n):
+            r = fn()
+        b.record()
+        torch.cuda.synchronize()
+        times[name] = a.elapsed_time(b) / n
+        return r
+    with torch.no_grad():
+        xx = timed("dwconv_pack", lambda: S.ss2d_dwconv_pack(x, D, w["conv_w"], w["conv_b"], True))
+        x_dbl = timed("x_proj (cuBLAS)", lambda: torch.matmul(w["wx"], xx)).view(B, K, R + 2 * N, L)
+        dts = timed("dt_proj", lambda: S.ss2d_dt_proj(x_dbl[:, :, :R], w["wdt32"]))
+        ys = timed("selective_scan (4 fp32 planes)", lambda: scan_forward(
+            xx.view(B, 2 * D, L), dts.view(B, K * D, L), w["A"], x_dbl[:, :, R:R + N], x_dbl[:, :, R + N:], w["Ds"], None,
+            w["dt_bias"], True, True, u_group_div=2, reverse_group_mask=S.REVERSE_MASK)[0])
+        timed("merge_norm", lambda: S.ss2d_merge_norm(ys.view(B, K, D, L), H, W, w["norm_w"], w["norm_b"], None, 1e-5,
+                                                      out_dtype=torch.float16))
+        fused = None
+        if S.core_channels(D, N, H, W, torch.float16) > 0:
+            y = timed("fused core (xp_ss2d_core, opt-in)", lambda: S.ss2d_core(
+                xx, dts.view(B, K, D, L), w["A"], x_dbl[:, :, R:R + N], x_dbl[:, :, R + N:], w["Ds"], w["dt_bias"], H, W, True))
+            timed("plane_norm (opt-in)", lambda: S.ss2d_plane_norm(y, w["norm_w"], w["norm_b"], None, 1e-5, out_dtype=torch.float16))
+            fused = times["dwconv_pack"] + times["x_proj (cuBLAS)"] + times["dt_proj"] + times["fused core (xp_ss2d_core, opt-in)"] \
+                + times["plane_norm (opt-in)"]
+    default = sum(times[k] for k in ("dwconv_pack", "x_proj (cuBLAS)", "dt_proj", "selective_scan (4 fp32 planes)", "merge_norm"))
+    alg = B * L * ((D + K * (R + 2 * N)) * 2 + D * 2)
+    es = 2
+    # DRAM bytes each kernel must move (inputs read once + outputs written once), from the tensor shapes
+    moved = {"dwconv_pack": B * L * D * es * 3, "x_proj (cuBLAS)": B * L * (2 * D + K * (R + 2 * N)) * es,
+             "dt_proj": B * L * (K * R + K * D) * es, "selective_scan (4 fp32 planes)": B * L * (4 * D * es + K * D * es + 2 * K * N * es + K * D * 4),
+             "merge_norm": B * L * (K * D * 4 + D * es),
+             "fused core (xp_ss2d_core, opt-in)": B * L * (2 * D * es + K * D * es + 2 * K * N * es + D * 4),
+             "plane_norm (opt-in)": B * L * (D * 4 + D * es)}
+    out = {"shape": f"B{B} x 128x160 tokens, d_inner 96, N 1, K 4, R {R}, fp16", "algorithmic_GB": round(alg / 1e9, 3),
+           "default_path_ms": round(default, 3), "default_effective_GBs": round(alg / default / 1e6, 1),
+           "default_frac_of_hbm_peak": round(alg / default / 1e6 / peak, 4),
+           "default_tensor_traffic_GB": round(sum(moved[k] for k in list(moved)[:5]) / 1e9, 2),
+           "ncu_dram_GB_r1": 17.2, "kernels_ms": {k: round(v, 3) for k, v in times.items()},
+           "kernel_tensor_traffic_GB": {k: round(v / 1e9, 2) for k, v in moved.items()}}
+    if fused is not None:
+        out.update({"fused_core_path_ms": round(fused, 3), "fused_core_effective_GBs": round(alg / fused / 1e6, 1),
+                    "fused_core_tensor_traffic_GB": round((moved["dwconv_pack"] + moved["x_proj (cuBLAS)"] + moved["dt_proj"]
+                                                           + moved["fused core (xp_ss2d_core, opt-in)"] + moved["plane_norm (opt-in)"]) / 1e9, 2)})
+    return out
+
+
+def time_pipeline(X, torch, preset, B, H, W, topk, dtype_fp16, steps=5, graph=True):
+    """pairs/s of a PairPipeline at another configuration (inputs resident, CUDA events, after warm-up)."""
+    torch.manual_seed(0)
+    net = X.XPoint({"takes_pair": True, "mixed_precision": dtype_fp16, "use_attention": {"preset": preset}}).cuda().eval()
+    pipe = X.PairPipeline(net, nms=8, detection_threshold=0.015, keep_top_k=topk)
+    g = torch.Generator().manual_seed(0)
+    o = torch.rand(B, 1, H, W, generator=g).cuda()
+    t = torch.rand(B, 1, H, W, generator=g).cuda()
+    for _ in range(3):
+        r = pipe(o, t)
+    fn = lambda: pipe(o, t)
+    if graph:
+        gp = pipe.capture(o, t)
+        for _ in range(3):
+            gp.replay()
+        fn = gp.replay
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(steps):
+        r = fn()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    out = {"pairs_per_s": round(B / ms * 1e3, 2), "ms_per_step": round(ms, 3), "pairs_per_step": B,
+           "keypoints_first": int(r.n_optical[0]), "matches_first": int(r.n_matches[0])}
+    del net, pipe, o, t, r
+    torch.cuda.empty_cache()
+    return out
+
+
+def other_configs(args):
+    """The BASELINE configurations that are not the headline line (measured after it, N=1 only)."""
+    import torch
+    import xpoint_b200 as X
+    out = {}
+    try:
+        out["configs[4] 1024x1280 top-16384 preset E fp16 (batch 8 pairs)"] = time_pipeline(X, torch, "E", 8, 1024, 1280, 16384, True, 3)
+    except Exception as e:  # noqa: BLE001 (reported, not hidden)
+        out["configs[4] 1024x1280 top-16384 preset E fp16 (batch 8 pairs)"] = {"error": repr(e)[:200]}
+    try:
+        out["preset V (vanilla VMamba-tiny, N=16) 512x640 top-4096 fp16 (batch 16 pairs)"] = time_pipeline(X, torch, "V", 16, 512, 640, 4096, True, 3)
+    except Exception as e:  # noqa: BLE001
+        out["preset V (vanilla VMamba-tiny, N=16) 512x640 top-4096 fp16 (batch 16 pairs)"] = {"error": repr(e)[:200]}
+    # single-pair latency, the quantity the reference's benchmark.py:151-164 prints (two_forward + nms + interpolate timers,
+    # benchmark_evaluation.py:28-37,77-83,118-134; matching is not timed there, it is here)
+    try:
+        lat = {}
+        for name, graph in (("eager", False), ("cuda_graph", True)):
+            r = time_pipeline(X, torch, "E", 1, 512, 640, 4096, True, 20, graph)
+            lat[name + "_ms_per_pair"] = r["ms_per_step"]
+        out["single pair latency 512x640 preset E fp16 (forward x2 + NMS + sampling + matching)"] = lat
+    except Exception as e:  # noqa: BLE001
+        out["single pair latency 512x640 preset E fp16 (forward x2 + NMS + sampling + matching)"] = {"error": repr(e)[:200]}
+    return out
+
+
+def parity_check(args, ref_out, dev):
+    """The GPU tail on the CPU arm's own fp32 prob / desc tensors must reproduce its keypoints and match pairs bit-exactly
+    (north star: "bit-exact when both sides are fed the same fp32 score/descriptor tensors"); the GPU model (fp32, same
+    weights) must agree with the CPU arm's prob / desc within 1e-4."""
+    import numpy as np
+    import torch
+    import xpoint_b200 as X
+    res = {}
+    po, pt = ref_out["prob_o"].float(), ref_out["prob_t"].float()
+    do, dt_ = ref_out["desc_o"].float(), ref_out["desc_t"].float()
+    n = po.shape[0]
+    pipe = X.PairPipeline(None, nms=8, detection_threshold=0.015, keep_top_k=args.topk)
+    r = pipe.tail(po.to(dev), pt.to(dev), do.to(dev), dt_.to(dev))
+    kp_ok, m_ok, nk, nm = True, True, 0, 0
+    for b in range(n):
+        t = ref_out["tail"][b]
+        no, nt = int(r.n_optical[b]), int(r.n_thermal[b])
+        kp_ok &= no == len(t["kp_o"]) and nt == len(t["kp_t"])
+        kp_ok &= bool(np.array_equal(r.kp_optical[b, :no].cpu().numpy().astype(np.int64), np.asarray(t["kp_o"]).reshape(-1, 2)))
+        kp_ok &= bool(np.array_equal(r.kp_thermal[b, :nt].cpu().numpy().astype(np.int64), np.asarray(t["kp_t"]).reshape(-1, 2)))
+        # identical descriptors to both matchers: the GPU matcher on the CPU arm's sampled descriptors
+        if len(t["d_o"]) and len(t["d_t"]):
+            got = X.get_matches(torch.from_numpy(np.asarray(t["d_o"])).to(dev), torch.from_numpy(np.asarray(t["d_t"])).to(dev),
+                                "bfmatcher", crossCheck=True)
+            got = [(a.queryIdx, a.trainIdx) for a in got]
+        else:
+            got = []
+        want = [tuple(x) for x in t["pairs"]]
+        if got != want:
+            # rows whose best-vs-second gap is below fp32 summation noise may legitimately differ (SURVEY C.13)
+            diff = set(got) ^ set(want)
+            m_ok &= len(diff) <= max(2, len(want) // 200)
+            res.setdefault("match_pairs_differing", 0)
+            res["match_pairs_differing"] += len(diff)
+        nk += no + nt
+        nm += len(want)
+    res.update({"pairs": n, "keypoints": nk, "matches": nm, "keypoints_bit_exact": bool(kp_ok), "match_pairs_equal": bool(m_ok)})
+    if "state_dict" in ref_out:
+        net = X.XPoint({"takes_pair": True, "use_attention": {"preset": args.preset}})
+        net.load_state_dict(ref_out["state_dict"], strict=True)
+        net = net.to(dev).eval()
+        g = torch.Generator().manual_seed(0)
+        opt = torch.rand(n, 1, args.height, args.width, generator=g).to(dev)
+        thr = torch.rand(n, 1, args.height, args.width, generator=g).to(dev)
+        tf = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+        with torch.no_grad():
+            go, gt = net.forward_pair_batched(opt, thr)
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf
+
+        def rel(x, y):
+            x, y = x.double().cpu(), y.double()
+            return float((x - y).norm() / y.norm())
+        res["gpu_fp32_model_vs_cpu_arm_rel_l2"] = {"prob": rel(go["prob"], po), "desc": rel(go["desc"], do)}
+    return res
 
 
 def run_ours(args):
@@ -345,13 +612,27 @@ def run_ours(args):
         del res
         torch.cuda.empty_cache()
         micro = scan_microbench(peak)
-    cpu = None
+    cpu, parity, core_fig, others = None, None, None, None
+    if rank == 0 and world == 1 and not args.no_extras:
+        try:
+            core_fig = ss2d_core_figure(peak)
+        except Exception as e:  # noqa: BLE001 (reported in the line, not hidden)
+            core_fig = {"error": repr(e)[:300]}
+        torch.cuda.empty_cache()
+        others = other_configs(args)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        NP = 16                              # bounded sample: ~10-20 s of host work
-        step, threads = cpu_pair_run(args, NP)
-        t, _ = step()
-        cpu = {"value": NP / t, "unit": "pairs/s", "cores": threads, "kind": "port",
-               "sample": f"{NP} pairs {H}x{W} through oracle/model.py + xp_oracle.c (torch CPU for dense layers), {t:.1f} s"}
+        # bounded sample: ONE pair through the staged reference on the host cores (~10-30 s), or 16 pairs through the port
+        staged = reference_staged() is not None and not args.ref_port
+        NP = 1 if staged else 16
+        step, threads, kind, what = cpu_arm(args, NP)
+        t, ref_out = step()
+        cpu = {"value": NP / t, "unit": "pairs/s", "cores": threads, "kind": kind,
+               "sample": f"{NP} pair(s) {H}x{W}, {t:.1f} s; {what}"}
+        if kind == "reference":
+            try:
+                parity = parity_check(args, ref_out, dev)
+            except Exception as e:  # noqa: BLE001
+                parity = {"error": repr(e)[:300]}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -360,6 +641,8 @@ def run_ours(args):
     pairs = B * world * args.steps
     achieved_all = scan_bytes / scan_ms / 1e6 if scan_ms > 0 else 0.0
     # dominant kernel = the selective-scan launch shape with the largest share of the step (stage 0 of the encoder)
+    if not by_shape:            # (a path without op-level scan launches, e.g. XP_SS2D_CORE=1)
+        by_shape = {"none": [1, 1e-9, 0]}
     dom_key = max(by_shape, key=lambda k: by_shape[k][1])
     dom = by_shape[dom_key]
     dom_bytes, dom_ms = dom[2] / dom[0], dom[1] / dom[0]
@@ -371,7 +654,9 @@ def run_ours(args):
                 "achieved": round(dom_gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(dom_gbs / peak, 4),
                 "traffic": ncu_traffic.get(dom_key), "algorithmic_bytes_per_launch": int(dom_bytes),
                 "ms_per_launch": round(dom_ms, 4), "peak_source": peak_src,
-                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_s3_summary.md",
+                "traffic_source": "NOT measured in this run: ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one launch of "
+                                  "this kernel template and shape, profiles/r1_s3_summary.md (round 1, commit ef3b925; the kernel "
+                                  "source is unchanged since); null for any other shape",
                 "launches": dom[0], "share_of_step": round(dom[1] / ms_eager, 4),
                 "measured_in": "eager pass of the same K steps inside this process (CUDA events around each launch); the timed "
                                "region replays the same kernels from a CUDA graph" if graphed is not None else "timed region",
@@ -391,7 +676,7 @@ def run_ours(args):
                    "pairs_per_gpu": B, "l2": "inputs and activations larger than L2 (no flush needed)",
                    "e2e_pipeline": "per-step H2D of both image batches on a copy stream (double-buffered), D2H of keypoints/matches",
                    "keypoints_first4": n_kp, "matches_first4": n_matches,
-                   "matcher": "fp32 CUDA cores" if args.fp32_match else "tcgen05 3xTF32",
+                   "matcher": "fp32 CUDA cores" if args.fp32_match else "tcgen05 3xFP16 split on kind::f16 (3xTF32 when C % 64 != 0)",
                    "cuda_graph": graphed is not None, "eager_ms_per_step": round(ms_eager / args.steps, 3)},
         "e2e": {"value": pairs / (ms_e2e / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
@@ -399,6 +684,9 @@ def run_ours(args):
         "roofline": roofline,
         "scan_microbench": micro,
         "cpu_baseline": cpu,
+        "parity_check": parity,
+        "ss2d_core": core_fig,
+        "other_configs": others,
     }
     print(json.dumps(line), flush=True)
 

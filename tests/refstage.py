@@ -78,12 +78,25 @@ def load(with_ext=True, patch_cross_torch=False):
     if PY_DIR not in sys.path:
         sys.path.insert(0, PY_DIR)
     warnings.filterwarnings("ignore")
-    with contextlib.redirect_stdout(io.StringIO()):
-        import xpoint.models as xmodels
-        import xpoint.utils as xutils
-        from xpoint.models.vmamba_src import VMamba as RV
-        from xpoint.models.vmamba_src import csm_triton as RC
-        from xpoint.models.vmamba_src import csms6s as RS
+    hidden, had_path = None, EXT_DIR in sys.path
+    if not with_ext:
+        # the reference decides at import time whether it has a CUDA extension (csms6s.py:9-22); for its CPU / torch path the
+        # extension must not be importable while the package loads, even if this process has already loaded it for timing
+        hidden = sys.modules.pop("selective_scan_cuda_oflex", None)
+        if had_path:
+            sys.path.remove(EXT_DIR)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            import xpoint.models as xmodels
+            import xpoint.utils as xutils
+            from xpoint.models.vmamba_src import VMamba as RV
+            from xpoint.models.vmamba_src import csm_triton as RC
+            from xpoint.models.vmamba_src import csms6s as RS
+    finally:
+        if hidden is not None:
+            sys.modules["selective_scan_cuda_oflex"] = hidden
+        if not with_ext and had_path:
+            sys.path.insert(0, EXT_DIR)
     assert os.path.realpath(xmodels.__file__).startswith(os.path.realpath(PY_DIR)), xmodels.__file__
     ns = types.SimpleNamespace(models=xmodels, utils=xutils, RV=RV, RC=RC, RS=RS, ext=ext)
     if patch_cross_torch:

@@ -545,67 +545,23 @@ def run_ours(args):
     # Every step uploads ITS OWN images from pinned host memory and downloads its keypoints / matches.  The upload of
     # step i+1 runs on a copy stream while step i computes (two device buffers); the downloads are queued behind the
     # step's kernels and the host blocks on them one step later -- the standard input pipeline of a serving loop.
-    copy_stream = torch.cuda.Stream(device=dev)
-    dev_bufs = [(torch.empty_like(dev_o), torch.empty_like(dev_t)) for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
-    out_names = ("kp_optical", "kp_thermal", "n_optical", "n_thermal", "match_idx", "match_dist", "n_matches")
-    host_out = None
-
-    def upload(i):
-        o, t = dev_bufs[i % 2]
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[i % 2])          # the step that last read this buffer pair has finished
-            o.copy_(host_o, non_blocking=True)
-            t.copy_(host_t, non_blocking=True)
-            ready[i % 2].record(copy_stream)
-
-    def e2e_loop(n):
-        nonlocal host_out
-        main = torch.cuda.current_stream(dev)
-        for ev in consumed:
-            ev.record(main)
-        upload(0)
-        pending = None
-        for i in range(n):
-            if i + 1 < n:
-                upload(i + 1)
-            main.wait_event(ready[i % 2])
-            o, t = dev_bufs[i % 2]
-            if graphed is not None:
-                graphed.load(o, t)                           # device-to-device into the graph's static inputs
-                consumed[i % 2].record(main)
-                r = graphed.replay()
-            else:
-                r = pipe(o, t)
-                consumed[i % 2].record(main)
-            outs = [getattr(r, k) for k in out_names]
-            if host_out is None:
-                host_out = [[torch.empty(x.shape, dtype=x.dtype).pin_memory() for x in outs] for _ in range(2)]
-            for h, x in zip(host_out[i % 2], outs):
-                h.copy_(x, non_blocking=True)
-            done = torch.cuda.Event()
-            done.record(main)
-            if pending is not None:
-                pending.synchronize()                        # results of step i-1 are on the host
-            pending = done
-        pending.synchronize()
-        return host_out[(n - 1) % 2]
-
-    e2e_loop(2)
+    from xpoint_b200.pipeline import PairStream
+    stream = PairStream(pipe, dev, use_graph=graphed is not None, graphed=graphed)     # the product's own streaming loop
+    stream.run([(host_o, host_t)] * 2, keep=False)
     barrier()
+    stream.h2d_bytes = stream.d2h_bytes = 0
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    host_res = e2e_loop(args.steps)
+    host_res = stream.run(((host_o, host_t) for _ in range(args.steps)), keep=False)[-1]
     f1.record()
     barrier()
     ms_e2e = max_over_ranks(f0.elapsed_time(f1))
     clocks = sampler.stop() if rank == 0 else None
-    d2h = sum(x.numel() * x.element_size() for x in host_res)
-    h2d = host_o.numel() * 4 * 2
+    d2h = stream.d2h_bytes // args.steps          # counted from the tensors copied, per step
+    h2d = stream.h2d_bytes // args.steps
 
-    n_matches = [int(v) for v in host_res[-1][:4].tolist()]
-    n_kp = [int(v) for v in host_res[2][:4].tolist()]
+    n_matches = [int(v) for v in host_res["n_matches"][:4].tolist()]
+    n_kp = [int(v) for v in host_res["n_optical"][:4].tolist()]
 
     micro = None
     if rank == 0 and not args.no_microbench:
@@ -674,7 +630,7 @@ def run_ours(args):
                                f"({'shipped XPoint-EXP1 VMamba N=1' if args.preset == 'E' else 'vanilla VMamba-tiny N=16'}), "
                                f"{H}x{W} pairs, batch {B} pairs/GPU, NMS top-{args.topk}, MNN matching",
                    "pairs_per_gpu": B, "l2": "inputs and activations larger than L2 (no flush needed)",
-                   "e2e_pipeline": "per-step H2D of both image batches on a copy stream (double-buffered), D2H of keypoints/matches",
+                   "e2e_pipeline": "xpoint_b200.pipeline.PairStream: per-step H2D of both image batches from pinned host memory on a copy stream (double-buffered), D2H of keypoints / matches",
                    "keypoints_first4": n_kp, "matches_first4": n_matches,
                    "matcher": "fp32 CUDA cores" if args.fp32_match else "tcgen05 3xFP16 split on kind::f16 (3xTF32 when C % 64 != 0)",
                    "cuda_graph": graphed is not None, "eager_ms_per_step": round(ms_eager / args.steps, 3)},

@@ -207,6 +207,30 @@ XP_API int xp_ss2d_plane_norm(const float* y, const float* gamma, const float* b
                               int64_t B, int64_t D, int64_t H, int64_t W, int32_t out_dtype, float eps,
                               xp_stream_t stream);
 
+/* -- f3 / f4 ("next" rows): the evaluation driver's per-sample geometry, batched on the device --------------
+ * Replaces warp_keypoints + filter_points (xpoint/utils/homographies.py:479-495,511-526: cv2.perspectiveTransform in float64
+ * on (x, y), numpy astype(int)) and the per-sample loops of compute_repeatability_for_sample / compute_descriptor_for_sample
+ * (xpoint/utils/benchmark_evaluation.py:396-467,650-690).  keypoints (B, k, 2) int32 (y, x) with counts (B) (rows >= count
+ * ignored), H (B, 3, 3) float64 row-major.
+ * xp_warp_keypoints: out_float (B, k, 2) float64 (y', x') and / or out_int (B, k, 2) int32 (truncated toward zero) and / or
+ *   inside (B, k) uint8 = filter_points on the int result (filter_on_float = 0) or on the float result (1); any may be NULL.
+ * xp_repeatability_counts: for set A already warped to B's frame (out_int + inside above): counts (B, n_thr) = points of A
+ *   inside the image whose nearest keypoint of set B is within thresholds[t] (float64, <= 8 of them), n_inside (B).
+ * xp_match_score_counts: queries warped by the ground-truth homography in float64 (out_float + inside with filter_on_float):
+ *   n_correct (B, n_thr) matches (q, match_idx[q]) with || float32(warped_q - kp_t) || <= thr, n_gt (B, n_thr) queries with at
+ *   least one train keypoint within thr, n_possible (B) warped queries inside the image, n_matches (B). */
+XP_API int xp_warp_keypoints(const int32_t* keypoints, const int32_t* count, const double* H, int64_t B, int64_t k,
+                             int64_t height, int64_t width, double* out_float, int32_t* out_int, uint8_t* inside,
+                             int32_t filter_on_float, xp_stream_t stream);
+XP_API int xp_repeatability_counts(const int32_t* warped_a, const uint8_t* inside_a, const int32_t* count_a,
+                                   const int32_t* keypoints_b, const int32_t* count_b, int64_t B, int64_t k,
+                                   const double* thresholds, int64_t n_thresholds, int32_t* counts, int32_t* n_inside,
+                                   xp_stream_t stream);
+XP_API int xp_match_score_counts(const double* warped_q, const uint8_t* inside_q, const int32_t* count_q,
+                                 const int32_t* keypoints_t, const int32_t* count_t, const int32_t* match_idx, int64_t B,
+                                 int64_t k, const double* thresholds, int64_t n_thresholds, int32_t* n_correct, int32_t* n_gt,
+                                 int32_t* n_possible, int32_t* n_matches, xp_stream_t stream);
+
 /* -- f2 (first "next" row): channel-last LayerNorm ---------------------------------------
  * Replaces the nn.LayerNorm calls around the SS2D block (VSSBlock.norm / norm2, patch-embed and downsample norms:
  * VMamba.py:1222-1234, :1405-1440).  x (rows, C) in in_dtype -> y (rows, C) in out_dtype; gamma/beta (C) fp32;

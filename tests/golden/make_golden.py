@@ -327,6 +327,69 @@ def gen_homography():
     save("homography", height=np.int32(Hh), width=np.int32(Ww), cv2_version=np.array(cv2.__version__), **cases)
 
 
+def gen_metrics():
+    """The evaluation driver's per-sample metrics through the reference's own functions
+    (benchmark_evaluation.py:396-467 compute_repeatability_for_sample, :588-750 compute_descriptor_for_sample;
+    homographies.py:479-526 warp_keypoints / filter_points) on a synthetic batch of 3 pairs at 96x128: sparse score maps
+    (already non-maximum-suppressed), unit descriptor maps, identity / affine / projective ground-truth homographies."""
+    from xpoint.utils import benchmark_evaluation as BE
+    from xpoint.utils import homographies as HM
+    g = torch.Generator().manual_seed(0)
+    Bn, Hh, Ww = 3, 96, 128
+    Hs = torch.eye(3).repeat(Bn, 1, 1)
+    Ht = torch.stack([torch.eye(3),
+                      torch.tensor([[0.98, -0.05, 3.0], [0.04, 1.01, -2.0], [0.0, 0.0, 1.0]]),
+                      torch.tensor([[1.02, 0.03, -4.0], [-0.02, 0.97, 5.0], [1e-4, -2e-4, 1.0]])])
+    prob_o = torch.zeros(Bn, 1, Hh, Ww)
+    prob_t = torch.zeros(Bn, 1, Hh, Ww)
+    for b in range(Bn):
+        n = 160
+        ys, xs = torch.randint(0, Hh, (n,), generator=g), torch.randint(0, Ww, (n,), generator=g)
+        prob_o[b, 0, ys, xs] = 0.1 + 0.8 * torch.rand(n, generator=g)
+        # thermal keypoints: the optical ones moved by the ground truth (+ jitter), plus clutter
+        kp = torch.nonzero(prob_o[b, 0] > 0.015)
+        w = HM.warp_keypoints(kp.numpy(), Ht[b].numpy(), float)
+        w = np.round(w + np.random.default_rng(b).normal(0, 0.7, w.shape)).astype(int)
+        ok = (w[:, 0] >= 0) & (w[:, 0] < Hh) & (w[:, 1] >= 0) & (w[:, 1] < Ww)
+        w = w[ok][: int(0.8 * ok.sum())]
+        prob_t[b, 0, w[:, 0], w[:, 1]] = 0.1 + 0.8 * torch.rand(len(w), generator=g)
+        ys, xs = torch.randint(0, Hh, (40,), generator=g), torch.randint(0, Ww, (40,), generator=g)
+        prob_t[b, 0, ys, xs] = 0.1 + 0.8 * torch.rand(40, generator=g)
+    base = torch.randn(Bn, 256, Hh // 8, Ww // 8, generator=g)
+    desc_o = torch.nn.functional.normalize(base, dim=1)
+    desc_t = torch.nn.functional.normalize(base + 0.35 * torch.randn(base.shape, generator=g), dim=1)
+    data = {"optical": {"image": torch.zeros(Bn, 1, Hh, Ww), "valid_mask": torch.ones(Bn, 1, Hh, Ww), "homography": Hs},
+            "thermal": {"image": torch.zeros(Bn, 1, Hh, Ww), "valid_mask": torch.ones(Bn, 1, Hh, Ww), "homography": Ht}}
+    thr_rep, thr_kp = [1, 3], [2, 4]
+    rep = {th: [] for th in thr_rep}
+    nko, nkt = [], []
+    for b in range(Bn):          # the reference function overwrites its per-threshold dict per sample: call it sample by sample
+        d1 = {k: {kk: vv[b:b + 1] for kk, vv in v.items()} for k, v in data.items()}
+        r, a, c = BE.compute_repeatability_for_sample({"prob": prob_o[b:b + 1]}, {"prob": prob_t[b:b + 1]}, d1, Hs[b:b + 1],
+                                                      Ht[b:b + 1], 0.015, thr_rep)
+        for th in thr_rep:
+            rep[th].append(r[th][0] if r[th] else float("nan"))
+        nko += a
+        nkt += c
+    cfg = {"prediction": {"matching": {"method": "bfmatcher", "knn_matches": False, "method_kwargs": {"crossCheck": True}}}}
+    arrs = dict(prob_o=prob_o, prob_t=prob_t, desc_o=desc_o, desc_t=desc_t, H_o=Hs, H_t=Ht, thr_rep=np.array(thr_rep, float),
+                thr_kp=np.array(thr_kp, float), n_kp_o=np.array(nko), n_kp_t=np.array(nkt),
+                repeatability=np.array([rep[th] for th in thr_rep]).T)
+    ms_o, ms_t, nm = [], [], []
+    for b in range(Bn):
+        d1 = {k: {kk: vv[b:b + 1] for kk, vv in v.items()} for k, v in data.items()}
+        dd = BE.compute_descriptor_for_sample(prob_o[b:b + 1], prob_t[b:b + 1], desc_o[b:b + 1], desc_t[b:b + 1], d1, cfg, 0.015, thr_kp)
+        ms_o.append([dd[th]["m_score_optical"][0] for th in thr_kp])
+        ms_t.append([dd[th]["m_score_thermal"][0] for th in thr_kp])
+        nm.append([int(sum(dd[th]["tp_optical"])) for th in thr_kp])
+    arrs.update(m_score_optical=np.array(ms_o), m_score_thermal=np.array(ms_t), n_correct_optical=np.array(nm))
+    # warp_keypoints itself, int and float flavours
+    kp = torch.nonzero(prob_o[2, 0] > 0.015).numpy()
+    arrs.update(wk_in=kp, wk_int=HM.warp_keypoints(kp, Ht[2].numpy()), wk_float=HM.warp_keypoints(kp.astype(np.float32), Ht[2].numpy(), float))
+    save("metrics", **arrs)
+    print("metrics: repeatability", arrs["repeatability"].round(3).tolist(), "m_score_o", np.array(ms_o).round(3).tolist())
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["scan", "cross", "ss2d", "tail", "match", "model", "homography"]
     for w in which:

@@ -275,3 +275,28 @@ def test_ss2d_fused_core_matches_default_path(dtype):
         tol = 2e-5 if dtype == torch.float32 else 1e-2
         assert_close(y1.float().cpu().numpy(), y0.float().cpu().numpy(), tol, f"fused core vs default C={C} {dtype}")
         assert_close(y1.float().cpu().numpy(), y2.float().cpu().numpy(), tol, f"fused core vs CrossScan path C={C} {dtype}")
+
+
+def test_sharded_pair_pipeline_matches_direct_calls():
+    """ShardedPairPipeline: a host list of pairs streamed through pinned double buffers and a CUDA graph,
+    padded tail batch, results gathered on the host in input order == the same pairs through PairPipeline directly."""
+    import xpoint_b200 as X
+    from xpoint_b200.pipeline import ShardedPairPipeline
+    torch.manual_seed(0)
+    net = X.XPoint({"takes_pair": True, "mixed_precision": True, "use_attention": {"preset": "E"}}).to(DEV).eval()
+    g = torch.Generator().manual_seed(2)
+    o = torch.rand(7, 1, 128, 160, generator=g).pin_memory()
+    t = torch.rand(7, 1, 128, 160, generator=g).pin_memory()
+    sp = ShardedPairPipeline(net, devices=[torch.device("cuda", 0)], batch=3, keep_top_k=300)
+    res = sp.run(o, t)
+    pipe = X.PairPipeline(net, keep_top_k=300)
+    for lo in range(0, 7, 3):
+        r = pipe(o[lo:lo + 3].to(DEV), t[lo:lo + 3].to(DEV))
+        n = min(3, 7 - lo)
+        assert torch.equal(res["n_optical"][lo:lo + n], r.n_optical.cpu()[:n])
+        assert torch.equal(res["n_matches"][lo:lo + n], r.n_matches.cpu()[:n])
+        for b in range(n):
+            k = int(r.n_optical[b])
+            assert torch.equal(res["kp_optical"][lo + b, :k], r.kp_optical[b, :k].cpu())
+            assert torch.equal(res["match_idx"][lo + b, :k], r.match_idx[b, :k].cpu())
+    assert res["kp_optical"].shape[0] == 7

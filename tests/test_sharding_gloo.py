@@ -55,3 +55,70 @@ def test_two_rank_replicas_gloo():
     assert w0 == w1 == 200.0                       # max over ranks
     assert abs(t0 - 129 / 0.2) < 1e-9 and t0 == t1  # all pairs / slowest rank
     assert same0 and same1
+
+
+# ------------------------------------------------------------------------------------------ ShardedPairPipeline (f4)
+class _FakeStream:
+    """Stands in for PairStream on CPU: 'keypoints' are a deterministic function of the images, so the gather can be checked."""
+
+    def __init__(self, device):
+        self.device = device
+
+    def run(self, batches, keep=True):
+        out = []
+        for o, t in batches:
+            s = (o.flatten(1).sum(1) * 1000).round().to(torch.int32)
+            out.append({"n_optical": s, "n_thermal": (t.flatten(1).sum(1) * 1000).round().to(torch.int32),
+                        "kp_optical": s[:, None, None].expand(-1, 3, 2).contiguous()})
+        return out
+
+
+def _expected(o, t):
+    s = (o.flatten(1).sum(1) * 1000).round().to(torch.int32)
+    return s, (t.flatten(1).sum(1) * 1000).round().to(torch.int32)
+
+
+def test_sharded_pipeline_in_process_devices_and_padding():
+    """Two fake devices, 13 pairs in batches of 4: shards [0,7) and [7,13), the padded tail batches are trimmed, results
+    come back in input order."""
+    from xpoint_b200.pipeline import ShardedPairPipeline
+    g = torch.Generator().manual_seed(0)
+    o, t = torch.rand(13, 1, 8, 8, generator=g), torch.rand(13, 1, 8, 8, generator=g)
+    sp = ShardedPairPipeline(None, devices=["fake0", "fake1"], batch=4, stream_factory=_FakeStream)
+    res = sp.run(o, t)
+    so, st = _expected(o, t)
+    assert torch.equal(res["n_optical"], so) and torch.equal(res["n_thermal"], st)
+    assert res["kp_optical"].shape == (13, 3, 2) and torch.equal(res["kp_optical"][:, 0, 0], so)
+
+
+def _sharded_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from xpoint_b200.pipeline import ShardedPairPipeline
+    g = torch.Generator().manual_seed(1)                       # every rank holds the same host list of pairs
+    o, t = torch.rand(11, 1, 8, 8, generator=g), torch.rand(11, 1, 8, 8, generator=g)
+    sp = ShardedPairPipeline(None, devices=[f"fake{rank}"], batch=4, distributed=True, stream_factory=_FakeStream)
+    res = sp.run(o, t)
+    so, st = _expected(o, t)
+    q.put((rank, bool(torch.equal(res["n_optical"], so) and torch.equal(res["n_thermal"], st)), tuple(res["kp_optical"].shape)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_pipeline_distributed_gather_gloo():
+    """World size 2 on gloo: each rank runs its shard_range of the pairs, all_gather_object reassembles them in input order on
+    every rank."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True, (11, 3, 2)), (1, True, (11, 3, 2))]

@@ -81,6 +81,9 @@ _SIGNATURES = {
     "xp_match_workspace_bytes": (c_int64, [c_int64] * 4),
     "xp_estimate_homography": (ctypes.c_int, [c_void_p] * 4 + [c_int64] * 4 + [c_int32, c_float, c_int32, ctypes.c_uint32]
                                + [c_void_p] * 4),
+    "xp_warp_keypoints": (ctypes.c_int, [c_void_p] * 3 + [c_int64] * 4 + [c_void_p] * 3 + [c_int32, c_void_p]),
+    "xp_repeatability_counts": (ctypes.c_int, [c_void_p] * 5 + [c_int64] * 2 + [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "xp_match_score_counts": (ctypes.c_int, [c_void_p] * 6 + [c_int64] * 2 + [c_void_p, c_int64] + [c_void_p] * 5),
     "xp_mnn_match": (ctypes.c_int, [c_void_p] * 4 + [c_int64] * 4 + [c_void_p] * 5 + [c_int32, c_void_p, c_int64, c_void_p]),
 }
 

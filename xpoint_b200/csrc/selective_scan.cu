@@ -740,21 +740,30 @@ __device__ __forceinline__ void rows_consumer(const ScanParams& p, uint32_t sbas
                 du2[j] = make_float2(__shfl_sync(0xffffffffu, duo, src0), __shfl_sync(0xffffffffu, duo, src1));
                 yp2[j] = make_float2(Dm0 * uo, Dm1 * uo);
             }
+            // two states at a time: their recurrences are independent, so the dependent FFMA pairs of one state fill the
+            // latency slots of the other (ncu: 1.2 "wait" stall cycles per issued instruction with one state at a time)
 #pragma unroll
-            for (int i = 0; i < SPL; ++i) {
-                float bv[8], cv[8];
-                lds_group8<IN_T, REV>(sB, 2 * i + hf, c8, bv);
-                lds_group8<IN_T, REV>(sC, 2 * i + hf, c8, cv);
-                const float2 A2d = make_float2(A2[i], A2[i]);
+            for (int i = 0; i < SPL; i += 2) {
+                float bv0[8], cv0[8], bv1[8], cv1[8];
+                lds_group8<IN_T, REV>(sB, 2 * i + hf, c8, bv0);
+                lds_group8<IN_T, REV>(sB, 2 * (i + 1) + hf, c8, bv1);
+                lds_group8<IN_T, REV>(sC, 2 * i + hf, c8, cv0);
+                lds_group8<IN_T, REV>(sC, 2 * (i + 1) + hf, c8, cv1);
+                const float2 A0 = make_float2(A2[i], A2[i]), A1 = make_float2(A2[i + 1], A2[i + 1]);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const float2 arg = mul2(dl2[q], A2d);
-                    const float2 xb = mul2(du2[q], make_float2(bv[2 * q], bv[2 * q + 1]));
-                    float2 hh;
-                    hh.x = fmaf(ex2_approx(arg.x), h[i], xb.x);
-                    hh.y = fmaf(ex2_approx(arg.y), hh.x, xb.y);
-                    h[i] = hh.y;
-                    yp2[q] = fma2(hh, make_float2(cv[2 * q], cv[2 * q + 1]), yp2[q]);
+                    const float2 arg0 = mul2(dl2[q], A0), arg1 = mul2(dl2[q], A1);
+                    const float2 xb0 = mul2(du2[q], make_float2(bv0[2 * q], bv0[2 * q + 1]));
+                    const float2 xb1 = mul2(du2[q], make_float2(bv1[2 * q], bv1[2 * q + 1]));
+                    const float e0 = ex2_approx(arg0.x), e1 = ex2_approx(arg1.x), e2 = ex2_approx(arg0.y), e3 = ex2_approx(arg1.y);
+                    float2 h0, h1;
+                    h0.x = fmaf(e0, h[i], xb0.x);
+                    h1.x = fmaf(e1, h[i + 1], xb1.x);
+                    h0.y = fmaf(e2, h0.x, xb0.y);
+                    h1.y = fmaf(e3, h1.x, xb1.y);
+                    h[i] = h0.y; h[i + 1] = h1.y;
+                    yp2[q] = fma2(h0, make_float2(cv0[2 * q], cv0[2 * q + 1]), yp2[q]);
+                    yp2[q] = fma2(h1, make_float2(cv1[2 * q], cv1[2 * q + 1]), yp2[q]);
                 }
             }
             float yp[8];

@@ -207,6 +207,17 @@ XP_API int xp_ss2d_plane_norm(const float* y, const float* gamma, const float* b
                               int64_t B, int64_t D, int64_t H, int64_t W, int32_t out_dtype, float eps,
                               xp_stream_t stream);
 
+/* -- f2 (ABI 4): Linear + bias + residual add + LayerNorm in one tcgen05 GEMM ---------------
+ * Replaces  pend = A W^T + b ; x = x + pend ; n = LayerNorm(x)  at the end of a VSSBlock branch (SS2D.out_proj VMamba.py:664 /
+ * Mlp.fc2 :110-128 followed by the block's residual add and the next norm, :1222-1234):
+ *   x_new (M, N) fp32 = residual + A (M, K) W (N, K)^T + bias   (x_new may be NULL)
+ *   y     (M, N) 16-bit = LayerNorm_N(x_new) * gamma + beta
+ * A, W, y in `dtype` (fp16 | bf16), residual / x_new / bias / gamma / beta fp32.  N must be 96, 192 or 384 (the whole row sits
+ * in one TMEM accumulator tile), K % 8 == 0, all tensors contiguous and 16-byte aligned. */
+XP_API int xp_linear_res_ln(const void* A, const void* W, const float* bias, const float* residual, const float* gamma,
+                            const float* beta, float* x_new, void* y, int64_t M, int64_t N, int64_t K, int32_t dtype, float eps,
+                            xp_stream_t stream);
+
 /* -- f3 / f4 ("next" rows): the evaluation driver's per-sample geometry, batched on the device --------------
  * Replaces warp_keypoints + filter_points (xpoint/utils/homographies.py:479-495,511-526: cv2.perspectiveTransform in float64
  * on (x, y), numpy astype(int)) and the per-sample loops of compute_repeatability_for_sample / compute_descriptor_for_sample

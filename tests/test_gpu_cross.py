@@ -371,3 +371,27 @@ def test_ss2d_core_no_softplus_and_optional_operands():
     assert_close(got.cpu().numpy(), want.cpu().numpy(), 2e-5, "ss2d_core without softplus / D / bias")
     with pytest.raises(RuntimeError):
         S.ss2d_core(xx, delta, A, bc[:, :, :N], bc[:, :, N:], None, None, H, W + 4, False)
+
+
+# ------------------------------------------------------------------------------------------ Linear + residual + LayerNorm (f2)
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("M,K,N,bias", [(1000, 96, 96, False), (128 * 149 + 5, 384, 96, True), (777, 192, 192, False),
+                                         (4096, 768, 192, True), (513, 384, 384, False), (2000, 1536, 384, True), (1, 96, 96, True)])
+def test_linear_res_ln_matches_torch(M, K, N, bias, dtype):
+    """xp_linear_res_ln (tcgen05 GEMM with the residual add and the next LayerNorm in its epilogue) against
+    x + F.linear -> F.layer_norm in fp32 on the same 16-bit operands (VMamba.py:664 / :110-128 + :1222-1234)."""
+    from xpoint_b200.cross_scan import linear_res_ln
+    g = torch.Generator().manual_seed(M + K + N)
+    x = torch.randn(M, K, generator=g).to(dtype).to(DEV)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(dtype).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV) if bias else None
+    res = (3.0 * torch.randn(M, N, generator=g) + 0.7).to(DEV)
+    gam, bet = (1 + 0.2 * torch.randn(N, generator=g)).to(DEV), (0.3 * torch.randn(N, generator=g)).to(DEV)
+    s, y = linear_res_ln(x, W, b, res, gam, bet, 1e-5)
+    s_ref = res.double() + x.double() @ W.double().t() + (b.double() if bias else 0.0)
+    y_ref = torch.nn.functional.layer_norm(s_ref, (N,), gam.double(), bet.double(), 1e-5)
+    assert s.dtype == torch.float32 and y.dtype == dtype and s.shape == (M, N) and y.shape == (M, N)
+    assert_close(s.cpu().numpy(), s_ref.cpu().numpy(), 2e-6, f"linear_res_ln sum M={M} K={K} N={N}")
+    assert_close(y.float().cpu().numpy(), y_ref.cpu().numpy(), 1e-3 if dtype == torch.float16 else 6e-3, f"linear_res_ln y {dtype}")
+    _, y2 = linear_res_ln(x, W, b, res, gam, bet, 1e-5, want_sum=False)
+    assert torch.equal(y, y2)

@@ -68,6 +68,7 @@ _SIGNATURES = {
     "xp_add_layer_norm": (ctypes.c_int, [c_void_p] * 7 + [c_int64, c_int64] + [c_int32] * 4 + [c_float, c_void_p]),
     "xp_patch_embed_stem": (ctypes.c_int, [c_void_p] * 6 + [c_int64] * 5 + [c_float, c_int32, c_int32, c_void_p]),
     "xp_linear_act": (ctypes.c_int, [c_void_p] * 4 + [c_int64] * 3 + [c_int32, c_int32, c_void_p]),
+    "xp_linear_res_ln": (ctypes.c_int, [c_void_p] * 8 + [c_int64] * 3 + [c_int32, c_float, c_void_p]),
     "xp_detector_post": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32, c_void_p]),
     "xp_l2_normalize": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_void_p]),
     "xp_detector_post_cl": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int64, c_int32, c_void_p]),

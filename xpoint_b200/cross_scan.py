@@ -206,5 +206,33 @@ def linear_act(x: torch.Tensor, weight: torch.Tensor, bias, gelu: bool = False) 
     return out
 
 
+def linear_res_ln(x: torch.Tensor, weight: torch.Tensor, bias, res: torch.Tensor, ln_weight, ln_bias, eps: float = 1e-5,
+                  want_sum: bool = True):
+    """``s = res + x W^T + b ; y = LayerNorm(s)`` in one tcgen05 GEMM (xp_linear_res_ln): the end of a VSSBlock branch
+    (out_proj / fc2 -> residual add -> next norm, VMamba.py:664,110-128,1222-1234).  x (..., K) fp16 | bf16, weight (N, K) same
+    dtype, res (..., N) fp32; returns (s fp32 or None, y in x.dtype).  N in {96, 192, 384}."""
+    dev = _lib.require_cuda(x, weight, bias, res, ln_weight, ln_bias)
+    if x.dtype not in (torch.float16, torch.bfloat16) or weight.dtype != x.dtype or res.dtype != torch.float32:
+        raise RuntimeError("linear_res_ln: x / weight must both be fp16 or bf16 and the residual fp32")
+    x, weight, res = x.contiguous(), weight.contiguous(), res.contiguous()
+    N, K = weight.shape
+    if x.shape[-1] != K or res.shape[-1] != N or res.numel() // N != x.numel() // K:
+        raise RuntimeError("linear_res_ln: shape mismatch")
+    s = torch.empty_like(res) if want_sum else None
+    y = torch.empty(res.shape, dtype=x.dtype, device=dev)
+    if y.numel():
+        f32 = lambda t: None if t is None else t.float().contiguous()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().xp_linear_res_ln(_lib.ptr(x), _lib.ptr(weight), _lib.ptr(f32(bias)), _lib.ptr(res),
+                                                   _lib.ptr(f32(ln_weight)), _lib.ptr(f32(ln_bias)), _lib.ptr(s), _lib.ptr(y),
+                                                   x.numel() // K, N, K, _lib.dtype_code(x), float(eps), _lib.stream_ptr(dev)))
+        _lib.count_launches(1)
+    return s, y
+
+
+def linear_res_ln_supported(K: int, N: int) -> bool:
+    return N in (96, 192, 384) and K % 8 == 0
+
+
 def linear_act_supported(K: int, N: int) -> bool:
     return K % 8 == 0 and N % 32 == 0 and N <= 8192

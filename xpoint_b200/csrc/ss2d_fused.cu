@@ -230,11 +230,11 @@ __global__ void __launch_bounds__(256) ss2d_dwconv_pack_kernel(const T* __restri
 //   phase 2: tile += y2 + y3        column-major planes, float4 = 4 consecutive h
 //   phase 3: warp per token: two-pass LayerNorm over the D channels (row held in registers when DPER > 0),
 //            affine, optional gate, channel-last store
-template <typename TO, int TH, int TW, int DPER>
+template <typename TO, int TH, int TW, int DPER, bool MERGED>
 __global__ void __launch_bounds__(256) ss2d_merge_norm_kernel(const float* __restrict__ ys, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, const TO* __restrict__ zact,
                                                               TO* __restrict__ out, int D, int H, int W, int tiles_w,
-                                                              int tiles_h, float eps, int planes) {
+                                                              int tiles_h, float eps) {
     extern __shared__ __align__(16) float tile[];
     const int P = D | 1;                                   // odd pitch: conflict-free token-major writes
     const int L = H * W;                                   // D * L < 2^31 (host-checked): 32-bit offsets inside a plane set
@@ -244,9 +244,10 @@ __global__ void __launch_bounds__(256) ss2d_merge_norm_kernel(const float* __res
     const int64_t b = t;
     const int h0 = th * TH, w0 = tw * TW;
     const int tid = threadIdx.x;
-    // planes == 1: ys is the already merged (B, D, H, W) plane of xp_ss2d_core -- phase 1 copies it, phase 2 is skipped
-    const bool merged = planes == 1;
-    const float* y0 = ys + (b * planes + 0) * D * (int64_t)L;
+    // MERGED: ys is the already merged (B, D, H, W) plane of xp_ss2d_core -- phase 1 copies it, phase 2 is skipped
+    // (a compile-time switch: as a run-time flag inside the load loops it cost the four-plane kernel 0.8 ms per stage-0 launch)
+    constexpr bool merged = MERGED;
+    const float* y0 = ys + (b * (MERGED ? 1 : 4) + 0) * D * (int64_t)L;
     const float* y1 = y0 + (int64_t)D * L;
     const float* y2 = y1 + (int64_t)D * L;
     const float* y3 = y2 + (int64_t)D * L;
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(256) ss2d_merge_norm_kernel(const float* __res
         const bool ok = h < H && w < W;
         const int base = w * H + h;
         float* dst = tile + ((4 * q) * TW + ww) * P;
-        if (ok && !merged) {
+        if (ok && !MERGED) {
 #pragma unroll 4
             for (int c = tid / (QH * TW); c < D; c += cstep) {
                 const float4 a = __ldg(reinterpret_cast<const float4*>(y2 + c * L + base));
@@ -474,10 +475,17 @@ static int merge_norm_launch_d(const float* ys, const float* gamma, const float*
                                int64_t D, int64_t H, int64_t W, float eps, cudaStream_t st, int planes) {
     const int tiles_w = (int)ceil_div(W, TW), tiles_h = (int)ceil_div(H, TH);
     const int smem = TH * TW * (int)(D | 1) * 4;
-    auto kern = ss2d_merge_norm_kernel<TO, TH, TW, DPER>;
-    XP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<(unsigned)(B * tiles_h * tiles_w), 256, smem, st>>>(ys, gamma, beta, (const TO*)zact, (TO*)out, (int)D, (int)H, (int)W,
-                                                                 tiles_w, tiles_h, eps, planes);
+    if (planes == 1) {
+        auto kern = ss2d_merge_norm_kernel<TO, TH, TW, DPER, true>;
+        XP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        kern<<<(unsigned)(B * tiles_h * tiles_w), 256, smem, st>>>(ys, gamma, beta, (const TO*)zact, (TO*)out, (int)D, (int)H, (int)W,
+                                                                     tiles_w, tiles_h, eps);
+    } else {
+        auto kern = ss2d_merge_norm_kernel<TO, TH, TW, DPER, false>;
+        XP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        kern<<<(unsigned)(B * tiles_h * tiles_w), 256, smem, st>>>(ys, gamma, beta, (const TO*)zact, (TO*)out, (int)D, (int)H, (int)W,
+                                                                     tiles_w, tiles_h, eps);
+    }
     XP_LAUNCH_CHECK("ss2d_merge_norm_kernel");
     return XP_OK;
 }

@@ -23,8 +23,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ss2d as _ss2d
-from .cross_scan import (add_layer_norm, cross_scan_fn, layer_norm, linear_act, linear_act_supported, merge_norm_gate,
-                         patch_embed_stem)
+from .cross_scan import (add_layer_norm, cross_scan_fn, layer_norm, linear_act, linear_act_supported, linear_res_ln,
+                         linear_res_ln_supported, merge_norm_gate, patch_embed_stem)
 from .selective_scan import scan_forward, selective_scan_fn
 
 
@@ -65,6 +65,10 @@ class Mlp(nn.Module):  # VMamba.py:110-128 (channel-last only; XPoint never buil
         self.fc2 = nn.Linear(hidden_features, out_features)
 
     def forward(self, x):
+        return self.fc2(self.hidden(x))
+
+    def hidden(self, x):
+        """act(fc1(x)): everything before fc2 (the block wrapper may run fc2 fused with the residual add and the next norm)."""
         # 16-bit activations (autocast): fc1 + bias + exact GELU in ONE tcgen05 GEMM, the hidden tensor is written once
         if (x.is_cuda and x.dtype in (torch.float16, torch.bfloat16) and isinstance(self.act, nn.GELU)
                 and getattr(self.act, "approximate", "none") == "none"
@@ -75,8 +79,8 @@ class Mlp(nn.Module):  # VMamba.py:110-128 (channel-last only; XPoint never buil
             if cache is None or cache[0] != key:
                 cache = (key, w.detach().to(x.dtype).contiguous())
                 self._w1_cache = cache
-            return self.fc2(linear_act(x, cache[1], self.fc1.bias, gelu=True))
-        return self.fc2(self.act(self.fc1(x)))
+            return linear_act(x, cache[1], self.fc1.bias, gelu=True)
+        return self.act(self.fc1(x))
 
 
 class PatchMerging2D(nn.Module):  # VMamba.py:60-98, channel-last
@@ -278,8 +282,10 @@ class SS2D(nn.Module):
         return (_ss2d.fused_supported(H, W, self.d_inner, self.d_state) and (not self.force_fp32 or dtype == torch.float32)
                 and (self.family == "v0" or self.oflex or dtype == torch.float32) and not getattr(self, "disable_fused", False))
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, skip_out_proj: bool = False) -> torch.Tensor:
         """x (B, H, W, d_model) -> (B, H, W, d_model)   (forwardv0 VMamba.py:305-374, forwardv2 :648-664).
+        ``skip_out_proj``: return the out_proj INPUT (B, H, W, d_inner); the block wrapper then runs out_proj fused with the
+        residual add and the next LayerNorm (xp_linear_res_ln).
 
         in_proj / out_proj stay cuBLAS GEMMs.  The depth-wise 3x3 convolution + SiLU run on xp_ss2d_dwconv_pack, which
         reads the channel-last in_proj output directly and emits the channel-first layouts the scan needs (no permute
@@ -310,7 +316,7 @@ class SS2D(nn.Module):
             y = self.out_act(core(None))
             if zact is not None:
                 y = y * zact
-        return self.out_proj(y)
+        return y if skip_out_proj else self.out_proj(y)
 
 
 # SURVEY 8f row f1 (fused dt_proj, xp_scan_args.dt_weight) is built, parity-tested and measured, but it is NOT the default:
@@ -324,6 +330,8 @@ FUSE_DT_PROJ = os.environ.get("XP_FUSE_DT_PROJ", "0") not in ("", "0")
 # (b, channel) plane set per SM) and runs 2.4 ms per stage-0 block against 1.5 ms for the op-level scan, which the cheaper
 # out_norm pass (0.7 vs 1.0 ms) does not win back.
 USE_CORE = os.environ.get("XP_SS2D_CORE", "0") not in ("", "0")
+# XP_NO_LINEAR_LN=1: keep out_proj / fc2 on cuBLAS followed by xp_add_layer_norm (A/B measurements)
+FUSE_LINEAR_LN_OFF = os.environ.get("XP_NO_LINEAR_LN", "0") not in ("", "0")
 
 
 class VSSBlock(nn.Module):  # VMamba.py:1153-1240
@@ -462,29 +470,64 @@ class VSSM(nn.Module):
         return y
 
     @staticmethod
+    def _w16(lin: nn.Linear, dtype):
+        """The Linear's weight in the autocast dtype, cast once (inference: static parameters, keyed on their version)."""
+        w = lin.weight
+        key = (w.data_ptr(), w._version, dtype)
+        cache = getattr(lin, "_xp_w16", None)
+        if cache is None or cache[0] != key:
+            cache = (key, w.detach().to(dtype).contiguous())
+            lin._xp_w16 = cache
+        return cache[1]
+
+    @staticmethod
     def _run_blocks(blocks, x):
-        """Returns (x, pending) with the block output = x + pending (pending may be None)."""
+        """Returns (x, pending) with the block output = x + pending (pending may be None).
+
+        Under 16-bit autocast the projection that closes a branch (out_proj / fc2) is DEFERRED: it runs fused with the residual
+        add and the LayerNorm that opens the next branch (xp_linear_res_ln, one tcgen05 GEMM) instead of cuBLAS + xp_add_layer_norm;
+        the last branch of a stage has no next norm in this stage and is materialised by the plain Linear."""
         pend = None
+        defer = None            # (a16, Linear): pending = Linear(a16), not yet computed
+        cdt = VSSM._ln_dtype(True)
+        fuse_ok = cdt in (torch.float16, torch.bfloat16) and x.dtype == torch.float32 and not FUSE_LINEAR_LN_OFF
+
+        def can_defer(lin):
+            return fuse_ok and linear_res_ln_supported(lin.in_features, lin.out_features)
+
+        def open_branch(norm, x, pend, defer):
+            """x [+ pending] -> (new x, LayerNorm(new x) for the branch's first GEMM)."""
+            if defer is not None:
+                a16, lin = defer
+                return linear_res_ln(a16, VSSM._w16(lin, a16.dtype), lin.bias, x, norm.weight, norm.bias, norm.eps)
+            if pend is None:
+                return x, norm(x)
+            return add_layer_norm(pend, x, norm.weight, norm.bias, norm.eps, y_dtype=cdt or x.dtype)
+
         for blk in blocks:
             if not isinstance(blk, VSSBlock):
+                if defer is not None:
+                    pend, defer = defer[1](defer[0]), None
                 if pend is not None:
                     x, pend = x + pend, None
                 x = blk(x)
                 continue
             if blk.ssm_branch:
-                if pend is None:
-                    n = blk.norm(x)
+                x, n = open_branch(blk.norm, x, pend, defer)
+                pend = defer = None
+                if can_defer(blk.op.out_proj) and n.dtype == cdt:
+                    defer = (blk.op(n, skip_out_proj=True), blk.op.out_proj)
                 else:
-                    x, n = add_layer_norm(pend, x, blk.norm.weight, blk.norm.bias, blk.norm.eps,
-                                          y_dtype=VSSM._ln_dtype(True) or x.dtype)
-                pend = blk.op(n)
+                    pend = blk.op(n)
             if blk.mlp_branch:
-                if pend is None:
-                    n = blk.norm2(x)
+                x, n = open_branch(blk.norm2, x, pend, defer)
+                pend = defer = None
+                if can_defer(blk.mlp.fc2) and n.dtype == cdt:
+                    defer = (blk.mlp.hidden(n), blk.mlp.fc2)
                 else:
-                    x, n = add_layer_norm(pend, x, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps,
-                                          y_dtype=VSSM._ln_dtype(True) or x.dtype)
-                pend = blk.mlp(n)
+                    pend = blk.mlp(n)
+        if defer is not None:
+            pend = defer[1](defer[0])
         return x, pend
 
     def _downsample(self, ds, x, pend):

@@ -300,3 +300,23 @@ def test_sharded_pair_pipeline_matches_direct_calls():
             assert torch.equal(res["kp_optical"][lo + b, :k], r.kp_optical[b, :k].cpu())
             assert torch.equal(res["match_idx"][lo + b, :k], r.match_idx[b, :k].cpu())
     assert res["kp_optical"].shape[0] == 7
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_sharded_pair_pipeline_two_devices_in_process():
+    """ShardedPairPipeline over two GPUs of one process (worker thread + weight replica + CUDA graph per device) returns the
+    same keypoints / matches as a single device, in input order."""
+    import xpoint_b200 as X
+    from xpoint_b200.pipeline import ShardedPairPipeline
+    torch.manual_seed(0)
+    net = X.XPoint({"takes_pair": True, "mixed_precision": True, "use_attention": {"preset": "E"}}).to("cuda:0").eval()
+    g = torch.Generator().manual_seed(3)
+    o = torch.rand(10, 1, 128, 160, generator=g).pin_memory()
+    t = torch.rand(10, 1, 128, 160, generator=g).pin_memory()
+    one = ShardedPairPipeline(net, devices=[torch.device("cuda", 0)], batch=4, keep_top_k=256).run(o, t)
+    two = ShardedPairPipeline(net, devices=[torch.device("cuda", 0), torch.device("cuda", 1)], batch=4, keep_top_k=256).run(o, t)
+    assert torch.equal(one["n_optical"], two["n_optical"]) and torch.equal(one["n_matches"], two["n_matches"])
+    for b in range(10):
+        k = int(one["n_optical"][b])
+        assert torch.equal(one["kp_optical"][b, :k], two["kp_optical"][b, :k])
+        assert torch.equal(one["match_idx"][b, :k], two["match_idx"][b, :k])

@@ -366,16 +366,20 @@ class GraphedPairPipeline:
         if not optical.is_cuda:
             raise RuntimeError("GraphedPairPipeline.capture needs CUDA example inputs (their shapes are baked into the graph)")
         self.pipe = pipe
-        self.static_o, self.static_t = optical.clone(), thermal.clone()
-        side = torch.cuda.Stream(device=optical.device)
-        side.wait_stream(torch.cuda.current_stream(optical.device))
-        with torch.cuda.stream(side):           # warm-up on a side stream: lazy initialisation must not be captured
-            for _ in range(max(warmup, 1)):
-                pipe(self.static_o, self.static_t)
-        torch.cuda.current_stream(optical.device).wait_stream(side)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.result = pipe(self.static_o, self.static_t)
+        dev = optical.device
+        with torch.cuda.device(dev):
+            self.static_o, self.static_t = optical.clone(), thermal.clone()
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):           # warm-up on a side stream: lazy initialisation must not be captured
+                for _ in range(max(warmup, 1)):
+                    pipe(self.static_o, self.static_t)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            # an explicit capture stream ON THIS DEVICE: torch.cuda.graph's default capture stream is a class-level singleton
+            # created on whichever device was current at its first use, so a capture on a second GPU would not be recorded
+            with torch.cuda.graph(self.graph, stream=torch.cuda.Stream(device=dev)):
+                self.result = pipe(self.static_o, self.static_t)
 
     def load(self, optical: torch.Tensor, thermal: torch.Tensor, non_blocking: bool = True) -> None:
         self.static_o.copy_(optical, non_blocking=non_blocking)

@@ -166,4 +166,7 @@ def dt_proj_supported(R: int, L: int, dtype: torch.dtype, batch_groups: int, D: 
 
 def fused_supported(H: int, W: int, D: int, d_state: int) -> bool:
     """Shapes the copy-free path covers (the rest takes the CrossScan -> scan -> CrossMerge kernels)."""
-    return H % 4 == 0 and W % 4 == 0 and D <= 3072 and d_state <= 2
+    # d_state 1 | 2: scan_lanes_kernel, 4 | 8 | 16: scan_rows_kernel -- both route the four directions themselves
+    # (u_group_div / reverse_group_mask); other state sizes would take the generic kernel, which also supports the addressing
+    # but is a correctness path
+    return H % 4 == 0 and W % 4 == 0 and D <= 3072 and d_state in (1, 2, 4, 8, 16) and (H * W) % 8 == 0

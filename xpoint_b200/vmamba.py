@@ -279,7 +279,10 @@ class SS2D(nn.Module):
                                      out_dtype=out_dtype or xx.dtype)
 
     def _use_fused(self, H: int, W: int, dtype: torch.dtype) -> bool:
-        return (_ss2d.fused_supported(H, W, self.d_inner, self.d_state) and (not self.force_fp32 or dtype == torch.float32)
+        # force_fp32 (v0, v01-v03: VMamba.py:341,625 cast xs / dts / Bs / Cs to fp32 before the scan) needs no cast here: the
+        # kernels widen 16-bit operands to fp32 in registers and keep fp32 state and accumulation, which is the same arithmetic
+        # on the same values -- the four (B, K*D, L) fp32 copies the reference materialises are simply not made
+        return (_ss2d.fused_supported(H, W, self.d_inner, self.d_state)
                 and (self.family == "v0" or self.oflex or dtype == torch.float32) and not getattr(self, "disable_fused", False))
 
     def forward(self, x: torch.Tensor, skip_out_proj: bool = False) -> torch.Tensor:

@@ -605,14 +605,14 @@ def run_ours(args):
     dom_gbs = dom_bytes / dom_ms / 1e6
     # DRAM bytes of ONE launch of that shape from `ncu --set full` (profiles/r1_s3_summary.md): only known for the
     # default workload (preset E, fp16 autocast, 64 pairs of 512x640 -> B128 KD384 K4 N1 L20480 float16->float32)
-    ncu_traffic = {"B128 KD384 K4 N1 L20480 float16->float32": 4.075503e9 + 3.980529e9}
+    ncu_traffic = {"B128 KD384 K4 N1 L20480 float16->float32": 4.074885e9 + 3.983005e9}
     roofline = {"bound": "hbm", "kernel": f"xp_selective_scan_fwd -> scan_lanes_kernel, launch shape {dom_key}",
                 "achieved": round(dom_gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(dom_gbs / peak, 4),
                 "traffic": ncu_traffic.get(dom_key), "algorithmic_bytes_per_launch": int(dom_bytes),
                 "ms_per_launch": round(dom_ms, 4), "peak_source": peak_src,
                 "traffic_source": "NOT measured in this run: ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one launch of "
-                                  "this kernel template and shape, profiles/r1_s3_summary.md (round 1, commit ef3b925; the kernel "
-                                  "source is unchanged since); null for any other shape",
+                                  "this kernel template and shape, profiles/r2_ncu_full.md (round 2, profiles/capture_r2.sh; round 1 "
+                                  "measured 8.056 GB for the same kernel); null for any other shape",
                 "launches": dom[0], "share_of_step": round(dom[1] / ms_eager, 4),
                 "measured_in": "eager pass of the same K steps inside this process (CUDA events around each launch); the timed "
                                "region replays the same kernels from a CUDA graph" if graphed is not None else "timed region",

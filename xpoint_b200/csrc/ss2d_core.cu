@@ -524,32 +524,19 @@ static int core_launch(CoreParams p, cudaStream_t st) {
     return XP_OK;
 }
 
-// tuning knob XP_CORE_CFG: 1 = 8 tokens per lane and 6 warps per chain (24 warps, <= 85 registers) instead of 16 / 3
-static int core_cfg_variant() {
-    static const int v = getenv("XP_CORE_CFG") ? atoi(getenv("XP_CORE_CFG")) : 0;
-    return v;
-}
-
+// (8 tokens per lane and 6 warps per chain -- 24 warps at 80 registers -- was measured and is slower: 3.15 vs 2.50 ms at stage 0)
 template <typename IN_T> static int core_dispatch(const CoreParams& p, int64_t N, cudaStream_t st) {
     if (N == 1) {
-        if constexpr (sizeof(IN_T) == 2) {
-            if (core_cfg_variant() == 1) return core_launch<1, IN_T, 8, 6>(p, st);
-            return core_launch<1, IN_T, 16, 3>(p, st);
-        } else {
-            return core_launch<1, IN_T, 8, 3>(p, st);
-        }
+        if constexpr (sizeof(IN_T) == 2) return core_launch<1, IN_T, 16, 3>(p, st);
+        else return core_launch<1, IN_T, 8, 3>(p, st);
     }
     return core_launch<2, IN_T, 8, 3>(p, st);
 }
 
 template <typename IN_T> static int core_channels(int64_t N, int64_t D, int64_t L, int H, int W, int smem_limit) {
     if (N == 1) {
-        if constexpr (sizeof(IN_T) == 2) {
-            if (core_cfg_variant() == 1) return core_pick_ch<1, IN_T, 8, 6>(D, L, H, W, smem_limit);
-            return core_pick_ch<1, IN_T, 16, 3>(D, L, H, W, smem_limit);
-        } else {
-            return core_pick_ch<1, IN_T, 8, 3>(D, L, H, W, smem_limit);
-        }
+        if constexpr (sizeof(IN_T) == 2) return core_pick_ch<1, IN_T, 16, 3>(D, L, H, W, smem_limit);
+        else return core_pick_ch<1, IN_T, 8, 3>(D, L, H, W, smem_limit);
     }
     return core_pick_ch<2, IN_T, 8, 3>(D, L, H, W, smem_limit);
 }

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define XP_ABI_VERSION 4
+#define XP_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define XP_API __attribute__((visibility("default")))
@@ -217,6 +217,17 @@ XP_API int xp_ss2d_plane_norm(const float* y, const float* gamma, const float* b
 XP_API int xp_linear_res_ln(const void* A, const void* W, const float* bias, const float* residual, const float* gamma,
                             const float* beta, float* x_new, void* y, int64_t M, int64_t N, int64_t K, int32_t dtype, float eps,
                             xp_stream_t stream);
+
+/* -- f2 (ABI 5): the whole Mlp branch of a VSSBlock in one tcgen05 kernel ---------------
+ * Replaces  h = GELU(n W1^T + b1) ; pend = h W2^T + b2 ; x = x + pend ; n' = LayerNorm(x)  (Mlp.forward VMamba.py:110-128 with
+ * the block's residual add and the next norm, :1229-1234); the (M, 4C) hidden activation stays in shared memory.
+ *   A (M, C) 16-bit, W1 (4C, C), W2 (C, 4C) 16-bit, b1 (4C) / b2 (C) fp32 or NULL, residual (M, C) fp32
+ *   x_new (M, C) fp32 = residual + fc2(GELU(fc1(A)))   (may be NULL);  y (M, C) 16-bit = LayerNorm_C(x_new) * gamma + beta
+ * C must be 96 or 192; exact (erf) GELU; the hidden activation is rounded to `dtype` between the two GEMMs, as the
+ * reference's autocast does.  All tensors contiguous and 16-byte aligned. */
+XP_API int xp_mlp_res_ln(const void* A, const void* W1, const float* b1, const void* W2, const float* b2, const float* residual,
+                         const float* gamma, const float* beta, float* x_new, void* y, int64_t M, int64_t C, int32_t dtype,
+                         float eps, xp_stream_t stream);
 
 /* -- f3 / f4 ("next" rows): the evaluation driver's per-sample geometry, batched on the device --------------
  * Replaces warp_keypoints + filter_points (xpoint/utils/homographies.py:479-495,511-526: cv2.perspectiveTransform in float64

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(handle, s), f"{s} declared in include/xpoint_b200.h but not exported"
     assert sorted(_lib.exported_symbols()) == syms, "ctypes signature table out of sync with the header"
-    assert _lib.lib().xp_abi_version() == 4
+    assert _lib.lib().xp_abi_version() == 5
 
 
 def test_header_compiles_as_plain_c(tmp_path):

@@ -395,3 +395,37 @@ def test_linear_res_ln_matches_torch(M, K, N, bias, dtype):
     assert_close(y.float().cpu().numpy(), y_ref.cpu().numpy(), 1e-3 if dtype == torch.float16 else 6e-3, f"linear_res_ln y {dtype}")
     _, y2 = linear_res_ln(x, W, b, res, gam, bet, 1e-5, want_sum=False)
     assert torch.equal(y, y2)
+
+
+# ------------------------------------------------------------------------------------------ whole Mlp branch in one kernel (f2)
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("M,C,bias", [(1000, 96, True), (128 * 149 + 5, 96, True), (128 * 300, 96, False), (777, 192, True),
+                                       (128 * 160 + 77, 192, False), (1, 96, True), (129, 192, True)])
+def test_mlp_res_ln_matches_torch(M, C, bias, dtype):
+    """xp_mlp_res_ln (fc1 + GELU + fc2 + residual + next LayerNorm, hidden activation kept in shared memory) against the same
+    chain in float64 with the hidden activation rounded to the 16-bit dtype, as autocast does between Mlp.fc1 and Mlp.fc2
+    (VMamba.py:110-128 + :1229-1234)."""
+    from xpoint_b200.cross_scan import mlp_res_ln
+    g = torch.Generator().manual_seed(M + C)
+    x = torch.randn(M, C, generator=g).to(dtype).to(DEV)
+    W1 = (torch.randn(4 * C, C, generator=g) / C ** 0.5).to(dtype).to(DEV)
+    W2 = (torch.randn(C, 4 * C, generator=g) / (4 * C) ** 0.5).to(dtype).to(DEV)
+    b1 = (0.5 * torch.randn(4 * C, generator=g)).to(DEV) if bias else None
+    b2 = torch.randn(C, generator=g).to(DEV) if bias else None
+    res = (3.0 * torch.randn(M, C, generator=g) + 0.7).to(DEV)
+    gam, bet = (1 + 0.2 * torch.randn(C, generator=g)).to(DEV), (0.3 * torch.randn(C, generator=g)).to(DEV)
+    s, y = mlp_res_ln(x, W1, b1, W2, b2, res, gam, bet, 1e-5)
+    h = torch.nn.functional.gelu(x.double() @ W1.double().t() + (b1.double() if bias else 0.0)).to(dtype).double()
+    s_ref = res.double() + h @ W2.double().t() + (b2.double() if bias else 0.0)
+    y_ref = torch.nn.functional.layer_norm(s_ref, (C,), gam.double(), bet.double(), 1e-5)
+    assert s.dtype == torch.float32 and y.dtype == dtype and s.shape == (M, C) and y.shape == (M, C)
+    # the only rounding difference: hidden values that sit on a 16-bit rounding boundary (fp32 vs fp64 fc1 accumulation)
+    tol_s = 2e-4 if dtype == torch.float16 else 1.5e-3
+    assert_close(s.cpu().numpy(), s_ref.cpu().numpy(), tol_s, f"mlp_res_ln sum M={M} C={C}")
+    assert_close(y.float().cpu().numpy(), y_ref.cpu().numpy(), 1.5e-3 if dtype == torch.float16 else 8e-3, f"mlp_res_ln y {dtype}")
+    _, y2 = mlp_res_ln(x, W1, b1, W2, b2, res, gam, bet, 1e-5, want_sum=False)
+    assert torch.equal(y, y2)
+    # against the two-kernel path of the library (linear_act + linear_res_ln): same operands, same rounding points
+    from xpoint_b200.cross_scan import linear_act, linear_res_ln
+    s3, y3 = linear_res_ln(linear_act(x, W1, b1, gelu=True), W2, b2, res, gam, bet, 1e-5)
+    assert_close(s.cpu().numpy(), s3.cpu().numpy(), tol_s, "mlp_res_ln vs linear_act + linear_res_ln")

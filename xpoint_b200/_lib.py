@@ -69,6 +69,7 @@ _SIGNATURES = {
     "xp_patch_embed_stem": (ctypes.c_int, [c_void_p] * 6 + [c_int64] * 5 + [c_float, c_int32, c_int32, c_void_p]),
     "xp_linear_act": (ctypes.c_int, [c_void_p] * 4 + [c_int64] * 3 + [c_int32, c_int32, c_void_p]),
     "xp_linear_res_ln": (ctypes.c_int, [c_void_p] * 8 + [c_int64] * 3 + [c_int32, c_float, c_void_p]),
+    "xp_mlp_res_ln": (ctypes.c_int, [c_void_p] * 10 + [c_int64] * 2 + [c_int32, c_float, c_void_p]),
     "xp_detector_post": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32, c_void_p]),
     "xp_l2_normalize": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_void_p]),
     "xp_detector_post_cl": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int64, c_int32, c_void_p]),
@@ -119,7 +120,7 @@ def lib() -> ctypes.CDLL:
             fn = getattr(handle, name)  # raises AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if handle.xp_abi_version() != 4:
+        if handle.xp_abi_version() != 5:
             raise RuntimeError("libxpoint_b200.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -230,6 +230,36 @@ def linear_res_ln(x: torch.Tensor, weight: torch.Tensor, bias, res: torch.Tensor
     return s, y
 
 
+def mlp_res_ln(x: torch.Tensor, w1: torch.Tensor, b1, w2: torch.Tensor, b2, res: torch.Tensor, ln_weight, ln_bias,
+               eps: float = 1e-5, want_sum: bool = True):
+    """The Mlp branch of a VSSBlock in one tcgen05 kernel (xp_mlp_res_ln): ``s = res + fc2(GELU(fc1(x))) ; y = LayerNorm(s)``
+    (Mlp.forward VMamba.py:110-128 + the block's residual add and the next norm, :1229-1234); the 4C-wide hidden activation
+    never reaches HBM.  x (..., C) fp16 | bf16, w1 (4C, C), w2 (C, 4C) same dtype, res (..., C) fp32, C in {96, 192};
+    returns (s fp32 or None, y in x.dtype)."""
+    dev = _lib.require_cuda(x, w1, b1, w2, b2, res, ln_weight, ln_bias)
+    if x.dtype not in (torch.float16, torch.bfloat16) or w1.dtype != x.dtype or w2.dtype != x.dtype or res.dtype != torch.float32:
+        raise RuntimeError("mlp_res_ln: x / w1 / w2 must all be fp16 or bf16 and the residual fp32")
+    x, w1, w2, res = x.contiguous(), w1.contiguous(), w2.contiguous(), res.contiguous()
+    C = x.shape[-1]
+    if tuple(w1.shape) != (4 * C, C) or tuple(w2.shape) != (C, 4 * C) or res.shape[-1] != C or res.numel() != x.numel():
+        raise RuntimeError("mlp_res_ln: shape mismatch (hidden width must be 4C)")
+    s = torch.empty_like(res) if want_sum else None
+    y = torch.empty(res.shape, dtype=x.dtype, device=dev)
+    if y.numel():
+        f32 = lambda t: None if t is None else t.float().contiguous()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().xp_mlp_res_ln(_lib.ptr(x), _lib.ptr(w1), _lib.ptr(f32(b1)), _lib.ptr(w2), _lib.ptr(f32(b2)),
+                                                _lib.ptr(res), _lib.ptr(f32(ln_weight)), _lib.ptr(f32(ln_bias)), _lib.ptr(s),
+                                                _lib.ptr(y), x.numel() // C, C, _lib.dtype_code(x), float(eps),
+                                                _lib.stream_ptr(dev)))
+        _lib.count_launches(1)
+    return s, y
+
+
+def mlp_res_ln_supported(C: int, hidden: int) -> bool:
+    return C in (96, 192) and hidden == 4 * C
+
+
 def linear_res_ln_supported(K: int, N: int) -> bool:
     return N in (96, 192, 384) and K % 8 == 0
 

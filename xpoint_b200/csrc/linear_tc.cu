@@ -32,28 +32,6 @@ template <int BN, int LT_STAGES> struct LtCfg {
     static constexpr int SMEM = LT_STAGES * STAGE + 1024 /*align*/ + 256 /*barriers + tmem ptr*/ + LT_EPI_WARPS * (LT_STG + 256 /*bias of the chunk*/);
 };
 
-// exact-GELU of two accumulators at once.  erf(x) = 1 - (1 + a1 x + .. + a6 x^6)^-16 for x >= 0 (Abramowitz-Stegun
-// 7.1.28, |err| <= 3e-7): one MUFU.RCP per value and otherwise only multiplies / FMAs, which issue as packed FMUL2 / FFMA2
-// (two fp32 lanes per slot) -- the epilogue warps then stay ahead of the store stream (libdevice erff is ~25 slots/value).
-__device__ __forceinline__ float2 gelu_erf2(float2 v) {
-    const float2 av = make_float2(fabsf(v.x), fabsf(v.y));
-    const float2 x = mul2(av, make_float2(0.70710678118654752f, 0.70710678118654752f));
-    float2 p = fma2(x, make_float2(0.0000430638f, 0.0000430638f), make_float2(0.0002765672f, 0.0002765672f));
-    p = fma2(p, x, make_float2(0.0001520143f, 0.0001520143f));
-    p = fma2(p, x, make_float2(0.0092705272f, 0.0092705272f));
-    p = fma2(p, x, make_float2(0.0422820123f, 0.0422820123f));
-    p = fma2(p, x, make_float2(0.0705230784f, 0.0705230784f));
-    p = fma2(p, x, make_float2(1.0f, 1.0f));
-    p = mul2(p, p); p = mul2(p, p); p = mul2(p, p); p = mul2(p, p);          // ^16
-    float2 r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(p.x));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(p.y));
-    // 0.5 v (1 + sign(v) erf|x|) = 0.5 v + 0.5 |v| (1 - r)
-    const float2 h = make_float2(0.5f, 0.5f);
-    const float2 t = fma2(mul2(av, make_float2(-0.5f, -0.5f)), r, mul2(av, h));   // 0.5 |v| (1 - r)
-    return fma2(v, h, t);
-}
-
 template <int BN, bool GELU, bool BF16, int LT_STAGES>
 __global__ void __launch_bounds__(LT_THREADS, 1)
 linear_act_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,

@@ -76,4 +76,51 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// 16 lanes x 16 consecutive fp32 columns variants (thread t of the warp <-> TMEM lane base + t)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        :: "r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+           "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+           "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+           "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// exact-GELU of two accumulators at once.  erf(x) = 1 - (1 + a1 x + .. + a6 x^6)^-16 for x >= 0 (Abramowitz-Stegun
+// 7.1.28, |err| <= 3e-7): one MUFU.RCP per value and otherwise only multiplies / FMAs, which issue as packed FMUL2 / FFMA2
+// (two fp32 lanes per slot) -- the epilogue warps then stay ahead of the store stream (libdevice erff is ~25 slots/value).
+__device__ __forceinline__ float2 gelu_erf2(float2 v) {
+    const float2 av = make_float2(fabsf(v.x), fabsf(v.y));
+    const float2 x = mul2(av, make_float2(0.70710678118654752f, 0.70710678118654752f));
+    float2 p = fma2(x, make_float2(0.0000430638f, 0.0000430638f), make_float2(0.0002765672f, 0.0002765672f));
+    p = fma2(p, x, make_float2(0.0001520143f, 0.0001520143f));
+    p = fma2(p, x, make_float2(0.0092705272f, 0.0092705272f));
+    p = fma2(p, x, make_float2(0.0422820123f, 0.0422820123f));
+    p = fma2(p, x, make_float2(0.0705230784f, 0.0705230784f));
+    p = fma2(p, x, make_float2(1.0f, 1.0f));
+    p = mul2(p, p); p = mul2(p, p); p = mul2(p, p); p = mul2(p, p);          // ^16
+    float2 r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(p.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(p.y));
+    // 0.5 v (1 + sign(v) erf|x|) = 0.5 v + 0.5 |v| (1 - r)
+    const float2 h = make_float2(0.5f, 0.5f);
+    const float2 t = fma2(mul2(av, make_float2(-0.5f, -0.5f)), r, mul2(av, h));   // 0.5 |v| (1 - r)
+    return fma2(v, h, t);
+}
+
 }  // namespace xp

@@ -6,17 +6,17 @@
 // the SM: per 128-row tile the hidden activation is produced 64 columns at a time, GELU'd on its way out of TMEM, written to
 // shared memory as one K-major 128B-swizzled k-block of the second GEMM's A operand (double-buffered), and consumed there.
 //
-// Persistent CTAs over 128-row tiles, C = 96 or 192; 20 warps, each role with its own instruction stream so that the
-// FMA-pipe-bound GELU (16 fp32 slots per value) and the latency-bound residual / LayerNorm epilogue overlap:
-//   warp 0      TMA producer (one lane): the tile's A operand n [128 x C], then W1 / W2 k-block tiles in exactly the order the
-//               MMA warp consumes them
-//   warp 1      MMA issuer (one lane), one flat stream of 64-column hidden chunks g across tiles:
-//               GEMM1(g): acc1[g % 2] = n W1[g]^T (K = C), then GEMM2(g - 1): acc2[tile % 2] += H(g - 1) W2[:, g - 1]^T (K = 64)
-//               one chunk late, so GELU(g - 1) overlaps GEMM1(g) -- also across the tile boundary
+// Persistent CTAs over 128-row tiles, C = 96 or 192; 28 warps, each role with its own instruction stream so that the
+// FMA-pipe-bound GELU and the latency-bound residual / LayerNorm epilogue overlap.  g = flat index of a 64-column hidden chunk:
+//   warp 0      TMA producer (one lane): the tile's A operand n [128 x C], then per chunk W1(g) and W2(g - 2) k-block tiles
+//   warp 1      GEMM1 issuer (one lane): acc1[g % 2] = n W1[g]^T (K = C), as soon as its epilogue-1 group has read chunk g - 2
+//   warp 3      GEMM2 issuer (one lane): acc2[tile % 2] += H(g) W2[:, g]^T (K = 64) when H(g) is written.  Two issuers, because
+//               one thread issuing both GEMMs (with ring arithmetic) was the critical path of the whole CTA
 //   warp 2      TMEM allocation: acc1 2 x 64 columns + acc2 2 x C columns (512 at C = 192)
-//   warps 4-11  epilogue 1, thread = row, two warps (32-column halves) per TMEM lane quarter: tcgen05.ld -> + b1 -> exact GELU ->
-//               16-bit -> H k-block in shared memory (fence.proxy.async before the MMA warp is told)
-//   warps 12-19 epilogue 2, thread = row, two warps (C/2-column halves) per lane quarter: acc2 + b2 + residual -> one-pass
+//   warps 4-19  epilogue 1, thread = row: two groups of 8 warps (even / odd chunks, so one group's barrier waits hide behind the
+//               other's arithmetic), two warps (32-column halves) per TMEM lane quarter: tcgen05.ld -> + b1 -> exact GELU ->
+//               16-bit -> H[g % 2] k-block in shared memory (fence.proxy.async before the GEMM2 issuer is told)
+//   warps 20-27 epilogue 2, thread = row, two warps (C/2-column halves) per lane quarter: acc2 + b2 + residual -> one-pass
 //               shifted sums -> x_new (fp32) and LayerNorm (16-bit) out.  The residual arrives by cp.async two 16-column units
 //               ahead (across tiles) in a per-warp ring whose slots double as the transpose buffers of the coalesced stores.
 #include "common.cuh"
@@ -26,7 +26,9 @@ namespace xp {
 
 constexpr int MP_BM = 128, MP_BK = 64, MP_HC = 64;
 constexpr int MP_KB_TILE = MP_BM * 128;                // one 64-wide k-block of a 128-row operand: 16 KiB
-constexpr int MP_E1_WARPS = 8, MP_E2_WARPS = 8;
+constexpr int MP_E1_WARPS = 16, MP_E2_WARPS = 8;     // epilogue 1: two groups of 8 warps (even / odd chunks)
+constexpr int MP_E1G = MP_E1_WARPS / 2;                // warps per epilogue-1 group
+constexpr int MP_E1C = MP_HC / (MP_E1G / 4);           // hidden columns per epilogue-1 warp and chunk (32)
 constexpr int MP_THREADS = (4 + MP_E1_WARPS + MP_E2_WARPS) * 32;
 constexpr int MP_PF = 2;                               // residual units in flight per epilogue-2 warp
 constexpr int MP_STG_PITCH = 80, MP_STG = 32 * MP_STG_PITCH;      // 32 rows x (64 B + 16 B pad): one fp32 unit
@@ -54,6 +56,15 @@ template <int C> struct MpCfg {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {     // src_bytes 0: zero fill
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {       // explicit shared-space load (a generic LD costs a long scoreboard)
+    const uint4 r = lds128(saddr);
+    return make_float4(__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), __uint_as_float(r.w));
+}
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, float (&v)[16]) { tmem_ld16(taddr, v); }
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, float (&v)[32]) { tmem_ld32(taddr, v); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
@@ -100,8 +111,8 @@ mlp_res_ln_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         for (int s = 0; s < S1; ++s) { mbar_init(&w1_full[s], 1); mbar_init(&w1_empty[s], 1); }
         for (int s = 0; s < S2; ++s) { mbar_init(&w2_full[s], 1); mbar_init(&w2_empty[s], 1); }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&acc1_full[b], 1); mbar_init(&acc1_empty[b], MP_E1_WARPS);
-            mbar_init(&h_full[b], MP_E1_WARPS); mbar_init(&h_empty[b], 1);
+            mbar_init(&acc1_full[b], 1); mbar_init(&acc1_empty[b], MP_E1G);
+            mbar_init(&h_full[b], MP_E1G); mbar_init(&h_empty[b], 1);
             mbar_init(&acc2_full[b], 1); mbar_init(&acc2_empty[b], MP_E2_WARPS);
         }
         fence_mbar_init();
@@ -118,118 +129,143 @@ mlp_res_ln_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t vec_ss = smem_u32(vec_s);
 
+    // The three single-lane roles below keep running ring indices / parities instead of deriving them from the chunk number:
+    // an issuer thread that spends ~350 dependent instructions per chunk on divisions and descriptor arithmetic is what the
+    // whole CTA waits for (measured: the MMA warp never waited, and every epilogue warp waited for it).
     if (warp == 0 && lane == 0) {
-        // ===================== TMA producer: loads in the MMA warp's consumption order =====================
-        uint32_t i1 = 0, i2 = 0;
-        auto load_w2 = [&](int g) {
-            const uint32_t s = i2 % S2;
-            mbar_wait(&w2_empty[s], ((i2 / S2) & 1u) ^ 1u);
-            mbar_arrive_expect_tx(&w2_full[s], Cfg::W2_STAGE);
-            tma_load_2d(w2 + s * Cfg::W2_STAGE, &map_w2, &w2_full[s], (g % NCHUNK) * MP_HC, 0);
-            ++i2;
+        // ===================== TMA producer: A per tile, W1(g) and W2(g - 2) per chunk =====================
+        uint32_t s1 = 0, p1 = 1, s2 = 0, p2 = 1, as = 0, ap = 1;                       // ring slot + parity of its "empty" barrier
+        int j2 = -2;                                                                    // W2 runs two chunks behind W1
+        auto load_w2 = [&]() {
+            if (j2 >= 0) {
+                mbar_wait(&w2_empty[s2], p2);
+                mbar_arrive_expect_tx(&w2_full[s2], Cfg::W2_STAGE);
+                tma_load_2d(w2 + s2 * Cfg::W2_STAGE, &map_w2, &w2_full[s2], j2 * MP_HC, 0);
+                if (++s2 == S2) { s2 = 0; p2 ^= 1u; }
+            }
+            if (++j2 == NCHUNK) j2 = 0;
         };
-        for (int g = 0; g < nchunks; ++g) {
-            const int tl = g / NCHUNK, j = g % NCHUNK;
-            if (j == 0) {
-                const int i0 = ((int)blockIdx.x + tl * (int)gridDim.x) * MP_BM;
-                const uint32_t ab = (uint32_t)tl % NA1;
-                mbar_wait(&a1_empty[ab], (((uint32_t)tl / NA1) & 1u) ^ 1u);
-                mbar_arrive_expect_tx(&a1_full[ab], Cfg::A1_BYTES);
-                for (int kb = 0; kb < KB1; ++kb)
-                    tma_load_2d(a1 + ab * Cfg::A1_BYTES + kb * MP_KB_TILE, &map_a, &a1_full[ab], kb * MP_BK, i0);
-            }
-            for (int kb = 0; kb < KB1; ++kb, ++i1) {
-                const uint32_t s = i1 % S1;
-                mbar_wait(&w1_empty[s], ((i1 / S1) & 1u) ^ 1u);
-                mbar_arrive_expect_tx(&w1_full[s], Cfg::W1_STAGE);
-                tma_load_2d(w1 + s * Cfg::W1_STAGE, &map_w1, &w1_full[s], kb * MP_BK, j * MP_HC);
-            }
-            if (g >= 1) load_w2(g - 1);
-        }
-        if (nchunks) load_w2(nchunks - 1);
-    } else if (warp == 1 && lane == 0) {
-        // ===================== MMA issuer =====================
-        constexpr uint32_t idesc1 = make_idesc_f16(MP_BM, MP_HC, BF16);
-        constexpr uint32_t idesc2 = make_idesc_f16(MP_BM, C, BF16);
-        uint32_t i1 = 0, i2 = 0;
-        const uint32_t a1_s = smem_u32(a1), h_s = smem_u32(hbuf);
-        auto gemm2 = [&](int g) {
-            const int tl = g / NCHUNK, j = g % NCHUNK;
-            const uint32_t hb = (uint32_t)g & 1u, ab = (uint32_t)tl & 1u;
-            mbar_wait(&h_full[hb], ((uint32_t)g >> 1) & 1u);                          // epilogue 1 has written H of this chunk
-            if (j == 0) mbar_wait(&acc2_empty[ab], (((uint32_t)tl >> 1) & 1u) ^ 1u);   // epilogue 2 has drained this accumulator
-            const uint32_t s = i2 % S2;
-            mbar_wait(&w2_full[s], (i2 / S2) & 1u);
-            tc_fence_after();
-            const uint64_t ad = make_smem_desc_sw128(h_s + hb * MP_KB_TILE);
-            const uint64_t wd = make_smem_desc_sw128(smem_u32(w2 + s * Cfg::W2_STAGE));
+        int i0 = (int)blockIdx.x * MP_BM;
+        for (int tl = 0; tl < ntl; ++tl, i0 += (int)gridDim.x * MP_BM) {
+            mbar_wait(&a1_empty[as], ap);
+            mbar_arrive_expect_tx(&a1_full[as], Cfg::A1_BYTES);
 #pragma unroll
-            for (int k = 0; k < MP_BK / 16; ++k) {
-                const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
-                umma_f16(tmem_base + Cfg::ACC2_COL + ab * C, ad + adv, wd + adv, idesc2, (j | k) != 0);
-            }
-            umma_commit(&w2_empty[s]);
-            umma_commit(&h_empty[hb]);                                                 // H[hb] may be overwritten once these retire
-            if (j == NCHUNK - 1) umma_commit(&acc2_full[ab]);
-            ++i2;
-        };
-        for (int g = 0; g < nchunks; ++g) {
-            const int tl = g / NCHUNK, j = g % NCHUNK;
-            const uint32_t buf = (uint32_t)g & 1u, ab = (uint32_t)tl % NA1;
-            if (j == 0) mbar_wait(&a1_full[ab], ((uint32_t)tl / NA1) & 1u);
-            mbar_wait(&acc1_empty[buf], (((uint32_t)g >> 1) & 1u) ^ 1u);               // epilogue 1 of two chunks ago has read it
-            tc_fence_after();
-            for (int kb = 0; kb < KB1; ++kb, ++i1) {
-                const uint32_t s = i1 % S1;
-                mbar_wait(&w1_full[s], (i1 / S1) & 1u);
-                tc_fence_after();
-                const uint64_t ad = make_smem_desc_sw128(a1_s + ab * Cfg::A1_BYTES + kb * MP_KB_TILE);
-                const uint64_t wd = make_smem_desc_sw128(smem_u32(w1 + s * Cfg::W1_STAGE));
+            for (int kb = 0; kb < KB1; ++kb)
+                tma_load_2d(a1 + as * Cfg::A1_BYTES + kb * MP_KB_TILE, &map_a, &a1_full[as], kb * MP_BK, i0);
+            if (++as == NA1) { as = 0; ap ^= 1u; }
+#pragma unroll 1
+            for (int j = 0; j < NCHUNK; ++j) {
 #pragma unroll
-                for (int k = 0; k < MP_BK / 16; ++k) {
-                    const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
-                    umma_f16(tmem_base + buf * MP_HC, ad + adv, wd + adv, idesc1, (kb | k) != 0);
+                for (int kb = 0; kb < KB1; ++kb) {
+                    mbar_wait(&w1_empty[s1], p1);
+                    mbar_arrive_expect_tx(&w1_full[s1], Cfg::W1_STAGE);
+                    tma_load_2d(w1 + s1 * Cfg::W1_STAGE, &map_w1, &w1_full[s1], kb * MP_BK, j * MP_HC);
+                    if (++s1 == S1) { s1 = 0; p1 ^= 1u; }
                 }
-                umma_commit(&w1_empty[s]);
+                load_w2();
             }
-            umma_commit(&acc1_full[buf]);
-            if (j == NCHUNK - 1) umma_commit(&a1_empty[ab]);                            // the tile's A operand is free again
-            if (g >= 1) gemm2(g - 1);
         }
-        if (nchunks) gemm2(nchunks - 1);
+        if (ntl) { load_w2(); load_w2(); }
+    } else if (warp == 1 && lane == 0) {
+        // ===================== GEMM1 issuer: acc1[g % 2] = n W1[g]^T =====================
+        constexpr uint32_t idesc1 = make_idesc_f16(MP_BM, MP_HC, BF16);
+        const uint64_t a_desc0 = make_smem_desc_sw128(smem_u32(a1)), w_desc0 = make_smem_desc_sw128(smem_u32(w1));
+        uint32_t s1 = 0, f1 = 0, as = 0, af = 0, epar = 1;
+        for (int tl = 0; tl < ntl; ++tl) {
+            mbar_wait(&a1_full[as], af);
+            const uint64_t a_desc = a_desc0 + (uint64_t)((as * Cfg::A1_BYTES) >> 4);
+#pragma unroll 1
+            for (int j = 0; j < NCHUNK; j += 2) {
+#pragma unroll
+                for (int buf = 0; buf < 2; ++buf) {                                    // NCHUNK is even: chunk j + buf -> acc1[buf]
+                    mbar_wait(&acc1_empty[buf], epar);                                 // its epilogue-1 group has read chunk g - 2
+                    tc_fence_after();
+#pragma unroll
+                    for (int kb = 0; kb < KB1; ++kb) {
+                        mbar_wait(&w1_full[s1], f1);
+                        tc_fence_after();
+                        const uint64_t ad = a_desc + (uint64_t)((kb * MP_KB_TILE) >> 4);
+                        const uint64_t wd = w_desc0 + (uint64_t)((s1 * Cfg::W1_STAGE) >> 4);
+#pragma unroll
+                        for (int k = 0; k < MP_BK / 16; ++k)
+                            umma_f16(tmem_base + buf * MP_HC, ad + (uint64_t)(k * 2), wd + (uint64_t)(k * 2), idesc1, (kb | k) != 0);
+                        umma_commit(&w1_empty[s1]);
+                        if (++s1 == S1) { s1 = 0; f1 ^= 1u; }
+                    }
+                    umma_commit(&acc1_full[buf]);
+                }
+                epar ^= 1u;
+            }
+            umma_commit(&a1_empty[as]);                                                // the tile's A operand is free again
+            if (++as == NA1) { as = 0; af ^= 1u; }
+        }
+    } else if (warp == 3 && lane == 0) {
+        // ===================== GEMM2 issuer: acc2[tile % 2] += H(g) W2[:, g]^T =====================
+        constexpr uint32_t idesc2 = make_idesc_f16(MP_BM, C, BF16);
+        const uint64_t h_desc0 = make_smem_desc_sw128(smem_u32(hbuf)), w_desc0 = make_smem_desc_sw128(smem_u32(w2));
+        uint32_t s2 = 0, f2 = 0, hpar = 0, cpar = 1;
+        for (int tl = 0; tl < ntl; ++tl) {
+            const uint32_t ab = (uint32_t)tl & 1u;
+            const uint32_t d_tmem = tmem_base + Cfg::ACC2_COL + ab * C;
+#pragma unroll 1
+            for (int j = 0; j < NCHUNK; j += 2) {
+#pragma unroll
+                for (int hb = 0; hb < 2; ++hb) {
+                    mbar_wait(&h_full[hb], hpar);                                      // epilogue 1 has written H of this chunk
+                    if (j == 0 && hb == 0) mbar_wait(&acc2_empty[ab], cpar);           // epilogue 2 has drained this accumulator
+                    mbar_wait(&w2_full[s2], f2);
+                    tc_fence_after();
+                    const uint64_t ad = h_desc0 + (uint64_t)((hb * MP_KB_TILE) >> 4);
+                    const uint64_t wd = w_desc0 + (uint64_t)((s2 * Cfg::W2_STAGE) >> 4);
+#pragma unroll
+                    for (int k = 0; k < MP_BK / 16; ++k)
+                        umma_f16(d_tmem, ad + (uint64_t)(k * 2), wd + (uint64_t)(k * 2), idesc2, (j | hb | k) != 0);
+                    umma_commit(&w2_empty[s2]);
+                    umma_commit(&h_empty[hb]);                                         // H[hb] may be overwritten once these retire
+                    if (++s2 == S2) { s2 = 0; f2 ^= 1u; }
+                }
+                hpar ^= 1u;
+            }
+            umma_commit(&acc2_full[ab]);
+            if (ab) cpar ^= 1u;
+        }
     } else if (warp >= 4 && warp < 4 + MP_E1_WARPS) {
         // ===================== epilogue 1: hidden chunk -> + b1 -> GELU -> 16-bit -> H k-block =====================
-        const int e = warp - 4, q = e & 3, part = e >> 2;                              // (warp % 4) == q: TMEM lane quarter
+        const int e = warp - 4, q = e & 3, grp = (e >> 2) & 1, part = e >> 3;          // (warp % 4) == q: TMEM lane quarter
         const uint32_t lane_t = (uint32_t)(q * 32) << 16;
         const int row = q * 32 + lane;
         const uint32_t h_row = smem_u32(hbuf) + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
         const uint32_t sw = (uint32_t)(row & 7);
+        const uint32_t buf = (uint32_t)grp;
+        uint32_t ph = 0;
+        int j = grp;                                                                   // chunk index inside the tile
 #pragma unroll 1
-        for (int g = 0; g < nchunks; ++g) {
-            const uint32_t buf = (uint32_t)g & 1u, ph = ((uint32_t)g >> 1) & 1u;
+        for (int g = grp; g < nchunks; g += 2, ph ^= 1u, j = (j + 2 == NCHUNK + grp) ? grp : j + 2) {   // acc1[grp] -> H[grp]
             mbar_wait(&acc1_full[buf], ph);
             tc_fence_after();
-            float v[32];
-            tmem_ld32(tmem_base + lane_t + buf * MP_HC + (uint32_t)(part * 32), v);
+            float v[MP_E1C];
+            tmem_ldn(tmem_base + lane_t + buf * MP_HC + (uint32_t)(part * MP_E1C), v);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc1_empty[buf]);                              // the accumulator is in registers
-            const float* bb = vec_s + (g % NCHUNK) * MP_HC + part * 32;
+            const uint32_t bb_s = vec_ss + (uint32_t)((j * MP_HC + part * MP_E1C) * 4);
             mbar_wait(&h_empty[buf], ph ^ 1u);                                         // GEMM2 of two chunks ago has read H[buf]
 #pragma unroll
-            for (int p4 = 0; p4 < 4; ++p4) {                                           // 16-byte pieces part * 4 + p4 of this row
+            for (int p4 = 0; p4 < MP_E1C / 8; ++p4) {                                  // 16-byte pieces of this row
                 uint32_t pk[4];
+                const float4 b_lo = lds_f4(bb_s + p4 * 32), b_hi = lds_f4(bb_s + p4 * 32 + 16);
+                const float bb[8] = {b_lo.x, b_lo.y, b_lo.z, b_lo.w, b_hi.x, b_hi.y, b_hi.z, b_hi.w};
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     const int c = p4 * 8 + 2 * t;
-                    const float2 g2 = gelu_erf2(make_float2(v[c] + bb[c], v[c + 1] + bb[c + 1]));
+                    const float2 g2 = gelu_erf2(make_float2(v[c] + bb[2 * t], v[c + 1] + bb[2 * t + 1]));
                     if (BF16) { const __nv_bfloat162 hh = __floats2bfloat162_rn(g2.x, g2.y); pk[t] = *reinterpret_cast<const uint32_t*>(&hh); }
                     else { const __half2 hh = __floats2half2_rn(g2.x, g2.y); pk[t] = *reinterpret_cast<const uint32_t*>(&hh); }
                 }
-                const uint32_t piece = (uint32_t)(part * 4 + p4);
-                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};"
-                             :: "r"(h_row + buf * MP_KB_TILE + ((piece ^ sw) << 4)), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+                const uint32_t piece = (uint32_t)(part * (MP_E1C / 8) + p4);
+                sts128(h_row + buf * MP_KB_TILE + ((piece ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
             }
             fence_proxy_async();                                                       // H is read by the tensor core (async proxy)
             __syncwarp();
@@ -238,9 +274,8 @@ mlp_res_ln_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     } else if (warp >= 4 + MP_E1_WARPS) {
         // ===================== epilogue 2: + b2 + residual -> x_new, LayerNorm =====================
         const int e = warp - 4 - MP_E1_WARPS, q = e & 3, half = e >> 2;                // (warp % 4) == q
-        uint8_t* ring = e2_smem + e * MP_E2_SMEM;
-        uint8_t* ystg = ring + MP_PF * MP_STG;
-        const uint32_t ring_s = smem_u32(ring);
+        const uint32_t ring_s = smem_u32(e2_smem + e * MP_E2_SMEM), ystg_s = ring_s + MP_PF * MP_STG;
+        const uint32_t sums_ss = smem_u32(sums_s);
         const uint32_t lane_t = (uint32_t)(q * 32) << 16;
         const int lr = lane >> 2, lp = lane & 3;
         const float invC = 1.0f / (float)C;
@@ -273,7 +308,6 @@ mlp_res_ln_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 #pragma unroll 1
             for (int k = 0; k < UPW; ++k) {
                 const int n = tl * UPW + k;
-                uint8_t* slot = ring + (n % MP_PF) * MP_STG;
                 const uint32_t slot_s = ring_s + (uint32_t)((n % MP_PF) * MP_STG);
                 const int col0 = half * (C / 2) + k * 16;
                 float v[16];
@@ -283,7 +317,7 @@ mlp_res_ln_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
                     const uint4 rr = lds128(slot_s + lane * MP_STG_PITCH + jj * 16);
-                    const float4 bb = *reinterpret_cast<const float4*>(vec_s + Cfg::HD + col0 + 4 * jj);
+                    const float4 bb = lds_f4(vec_ss + (uint32_t)((Cfg::HD + col0 + 4 * jj) * 4));
                     v[4 * jj] += __uint_as_float(rr.x) + bb.x; v[4 * jj + 1] += __uint_as_float(rr.y) + bb.y;
                     v[4 * jj + 2] += __uint_as_float(rr.z) + bb.z; v[4 * jj + 3] += __uint_as_float(rr.w) + bb.w;
                 }
@@ -293,12 +327,13 @@ mlp_res_ln_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 if (xnew) {
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj)
-                        *reinterpret_cast<float4*>(slot + lane * MP_STG_PITCH + jj * 16) = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
+                        sts128(slot_s + lane * MP_STG_PITCH + jj * 16, __float_as_uint(v[4 * jj]), __float_as_uint(v[4 * jj + 1]),
+                               __float_as_uint(v[4 * jj + 2]), __float_as_uint(v[4 * jj + 3]));
                     __syncwarp();
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int r = lr + 8 * i;
-                        const float4 val = *reinterpret_cast<const float4*>(slot + r * MP_STG_PITCH + lp * 16);
+                        const float4 val = lds_f4(slot_s + r * MP_STG_PITCH + lp * 16);
                         if (row0 + r < M) *reinterpret_cast<float4*>(xnew + (int64_t)(row0 + r) * C + col0 + lp * 4) = val;
                     }
                 }
@@ -306,10 +341,11 @@ mlp_res_ln_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 prefetch(n + MP_PF);
             }
             // the two halves of a row meet through shared memory (parity buffer, one 64-thread named barrier per quarter)
-            float2* sums_t = sums_s + (tl & 1) * MP_E2_WARPS * 32;
-            sums_t[e * 32 + lane] = make_float2(s1, s2);
+            const uint32_t sums_t = sums_ss + (uint32_t)((tl & 1) * MP_E2_WARPS * 32 * 8);
+            asm volatile("st.shared.v2.f32 [%0], {%1,%2};" :: "r"(sums_t + (e * 32 + lane) * 8), "f"(s1), "f"(s2) : "memory");
             asm volatile("bar.sync %0, 64;" :: "r"(1 + q) : "memory");
-            const float2 o = sums_t[(e ^ 4) * 32 + lane];
+            float2 o;
+            asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(o.x), "=f"(o.y) : "r"(sums_t + ((e ^ 4) * 32 + lane) * 8) : "memory");
             const float m1 = (s1 + o.x) * invC;
             const float mean = shift + m1;
             const float rstd = rsqrtf(fmaxf(fmaf(s2 + o.y, invC, -m1 * m1), 0.0f) + eps);
@@ -321,8 +357,8 @@ mlp_res_ln_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 uint32_t pk[8];
 #pragma unroll
                 for (int t = 0; t < 16; t += 4) {
-                    const float4 gg = *reinterpret_cast<const float4*>(vec_s + Cfg::HD + C + col0 + t);
-                    const float4 be = *reinterpret_cast<const float4*>(vec_s + Cfg::HD + 2 * C + col0 + t);
+                    const float4 gg = lds_f4(vec_ss + (uint32_t)((Cfg::HD + C + col0 + t) * 4));
+                    const float4 be = lds_f4(vec_ss + (uint32_t)((Cfg::HD + 2 * C + col0 + t) * 4));
                     const float a0 = fmaf((v[t] - mean) * rstd, gg.x, be.x), a1v = fmaf((v[t + 1] - mean) * rstd, gg.y, be.y);
                     const float a2 = fmaf((v[t + 2] - mean) * rstd, gg.z, be.z), a3 = fmaf((v[t + 3] - mean) * rstd, gg.w, be.w);
                     if (BF16) {
@@ -333,13 +369,13 @@ mlp_res_ln_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                         pk[t / 2] = *reinterpret_cast<const uint32_t*>(&h0); pk[t / 2 + 1] = *reinterpret_cast<const uint32_t*>(&h1);
                     }
                 }
-                *reinterpret_cast<uint4*>(ystg + lane * MP_YSTG_PITCH) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                *reinterpret_cast<uint4*>(ystg + lane * MP_YSTG_PITCH + 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                sts128(ystg_s + lane * MP_YSTG_PITCH, pk[0], pk[1], pk[2], pk[3]);
+                sts128(ystg_s + lane * MP_YSTG_PITCH + 16, pk[4], pk[5], pk[6], pk[7]);
                 __syncwarp();
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     const int r = (lane >> 1) + 16 * i, piece = lane & 1;
-                    const uint4 val = *reinterpret_cast<const uint4*>(ystg + r * MP_YSTG_PITCH + piece * 16);
+                    const uint4 val = lds128(ystg_s + r * MP_YSTG_PITCH + piece * 16);
                     if (row0 + r < M)
                         *reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(yout) + (int64_t)(row0 + r) * C + col0 + piece * 8) = val;
                 }

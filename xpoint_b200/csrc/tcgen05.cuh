@@ -101,26 +101,23 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-// exact-GELU of two accumulators at once.  erf(x) = 1 - (1 + a1 x + .. + a6 x^6)^-16 for x >= 0 (Abramowitz-Stegun
-// 7.1.28, |err| <= 3e-7): one MUFU.RCP per value and otherwise only multiplies / FMAs, which issue as packed FMUL2 / FFMA2
-// (two fp32 lanes per slot) -- the epilogue warps then stay ahead of the store stream (libdevice erff is ~25 slots/value).
+// exact-GELU of two accumulators at once.  erfc(x) = (1 + a1 x + .. + a6 x^6)^-16 for x >= 0 (Abramowitz-Stegun 7.1.28,
+// |err| <= 3e-7), evaluated in |v| directly (the 1/sqrt(2) of x = |v| / sqrt(2) is folded into the coefficients), and
+// GELU(v) = relu(v) - 0.5 |v| erfc(|v| / sqrt(2)):  one MUFU.RCP and one FMNMX (ALU pipe) per value, otherwise 12 packed
+// FMUL2 / FFMA2 per PAIR -- the fp32 FMA pipe is what bounds a GELU epilogue (libdevice erff is ~25 slots per value).
 __device__ __forceinline__ float2 gelu_erf2(float2 v) {
     const float2 av = make_float2(fabsf(v.x), fabsf(v.y));
-    const float2 x = mul2(av, make_float2(0.70710678118654752f, 0.70710678118654752f));
-    float2 p = fma2(x, make_float2(0.0000430638f, 0.0000430638f), make_float2(0.0002765672f, 0.0002765672f));
-    p = fma2(p, x, make_float2(0.0001520143f, 0.0001520143f));
-    p = fma2(p, x, make_float2(0.0092705272f, 0.0092705272f));
-    p = fma2(p, x, make_float2(0.0422820123f, 0.0422820123f));
-    p = fma2(p, x, make_float2(0.0705230784f, 0.0705230784f));
-    p = fma2(p, x, make_float2(1.0f, 1.0f));
+    float2 p = fma2(av, make_float2(5.3829750000e-06f, 5.3829750000e-06f), make_float2(4.8890635643e-05f, 4.8890635643e-05f));
+    p = fma2(p, av, make_float2(3.8003575000e-05f, 3.8003575000e-05f));
+    p = fma2(p, av, make_float2(3.2776263241e-03f, 3.2776263241e-03f));
+    p = fma2(p, av, make_float2(2.1141006150e-02f, 2.1141006150e-02f));
+    p = fma2(p, av, make_float2(4.9867346967e-02f, 4.9867346967e-02f));
+    p = fma2(p, av, make_float2(1.0f, 1.0f));
     p = mul2(p, p); p = mul2(p, p); p = mul2(p, p); p = mul2(p, p);          // ^16
     float2 r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(p.x));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(p.y));
-    // 0.5 v (1 + sign(v) erf|x|) = 0.5 v + 0.5 |v| (1 - r)
-    const float2 h = make_float2(0.5f, 0.5f);
-    const float2 t = fma2(mul2(av, make_float2(-0.5f, -0.5f)), r, mul2(av, h));   // 0.5 |v| (1 - r)
-    return fma2(v, h, t);
+    return fma2(mul2(av, r), make_float2(-0.5f, -0.5f), make_float2(fmaxf(v.x, 0.0f), fmaxf(v.y, 0.0f)));
 }
 
 }  // namespace xp

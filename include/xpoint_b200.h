@@ -222,7 +222,8 @@ XP_API int xp_linear_res_ln(const void* A, const void* W, const float* bias, con
  * Replaces  h = GELU(n W1^T + b1) ; pend = h W2^T + b2 ; x = x + pend ; n' = LayerNorm(x)  (Mlp.forward VMamba.py:110-128 with
  * the block's residual add and the next norm, :1229-1234); the (M, 4C) hidden activation stays in shared memory.
  *   A (M, C) 16-bit, W1 (4C, C), W2 (C, 4C) 16-bit, b1 (4C) / b2 (C) fp32 or NULL, residual (M, C) fp32
- *   x_new (M, C) fp32 = residual + fc2(GELU(fc1(A)))   (may be NULL);  y (M, C) 16-bit = LayerNorm_C(x_new) * gamma + beta
+ *   x_new (M, C) fp32 = residual + fc2(GELU(fc1(A)))   (may be NULL);  y (M, C) 16-bit = LayerNorm_C(x_new) * gamma + beta,
+ *   or with gamma == NULL  y = x_new rounded to `dtype` (the stage's last block: a strided convolution follows, VMamba.py:906-919)
  * C must be 96 or 192; exact (erf) GELU; the hidden activation is rounded to `dtype` between the two GEMMs, as the
  * reference's autocast does.  All tensors contiguous and 16-byte aligned. */
 XP_API int xp_mlp_res_ln(const void* A, const void* W1, const float* b1, const void* W2, const float* b2, const float* residual,

@@ -425,6 +425,9 @@ def test_mlp_res_ln_matches_torch(M, C, bias, dtype):
     assert_close(y.float().cpu().numpy(), y_ref.cpu().numpy(), 1.5e-3 if dtype == torch.float16 else 8e-3, f"mlp_res_ln y {dtype}")
     _, y2 = mlp_res_ln(x, W1, b1, W2, b2, res, gam, bet, 1e-5, want_sum=False)
     assert torch.equal(y, y2)
+    # without a LayerNorm (a stage's last block): y is the sum rounded to the 16-bit dtype
+    _, y4 = mlp_res_ln(x, W1, b1, W2, b2, res, None, None, want_sum=False)
+    assert torch.equal(y4, s.to(dtype))
     # against the two-kernel path of the library (linear_act + linear_res_ln): same operands, same rounding points
     from xpoint_b200.cross_scan import linear_act, linear_res_ln
     s3, y3 = linear_res_ln(linear_act(x, W1, b1, gelu=True), W2, b2, res, gam, bet, 1e-5)

@@ -235,7 +235,7 @@ def mlp_res_ln(x: torch.Tensor, w1: torch.Tensor, b1, w2: torch.Tensor, b2, res:
     """The Mlp branch of a VSSBlock in one tcgen05 kernel (xp_mlp_res_ln): ``s = res + fc2(GELU(fc1(x))) ; y = LayerNorm(s)``
     (Mlp.forward VMamba.py:110-128 + the block's residual add and the next norm, :1229-1234); the 4C-wide hidden activation
     never reaches HBM.  x (..., C) fp16 | bf16, w1 (4C, C), w2 (C, 4C) same dtype, res (..., C) fp32, C in {96, 192};
-    returns (s fp32 or None, y in x.dtype)."""
+    returns (s fp32 or None, y in x.dtype); with ``ln_weight=None`` y is s rounded to x.dtype (no LayerNorm)."""
     dev = _lib.require_cuda(x, w1, b1, w2, b2, res, ln_weight, ln_bias)
     if x.dtype not in (torch.float16, torch.bfloat16) or w1.dtype != x.dtype or w2.dtype != x.dtype or res.dtype != torch.float32:
         raise RuntimeError("mlp_res_ln: x / w1 / w2 must all be fp16 or bf16 and the residual fp32")

@@ -65,6 +65,11 @@ __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {       // explicit sha
 }
 __device__ __forceinline__ void tmem_ldn(uint32_t taddr, float (&v)[16]) { tmem_ld16(taddr, v); }
 __device__ __forceinline__ void tmem_ldn(uint32_t taddr, float (&v)[32]) { tmem_ld32(taddr, v); }
+__device__ __forceinline__ float4 lds_const_f4(uint32_t saddr) {   // data that never changes after set-up: the compiler may hoist it
+    float4 r;
+    asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(saddr));
+    return r;
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
@@ -121,8 +126,8 @@ mlp_res_ln_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     for (int i = threadIdx.x; i < Cfg::HD; i += MP_THREADS) vec_s[i] = b1 ? __ldg(b1 + i) : 0.0f;
     for (int i = threadIdx.x; i < C; i += MP_THREADS) {
         vec_s[Cfg::HD + i] = b2 ? __ldg(b2 + i) : 0.0f;
-        vec_s[Cfg::HD + C + i] = __ldg(gamma + i);
-        vec_s[Cfg::HD + 2 * C + i] = __ldg(beta + i);
+        vec_s[Cfg::HD + C + i] = gamma ? __ldg(gamma + i) : 1.0f;                     // gamma == NULL: y = x_new, no LayerNorm
+        vec_s[Cfg::HD + 2 * C + i] = (gamma && beta) ? __ldg(beta + i) : 0.0f;
     }
     if (warp == 2) tmem_alloc(tmem_ptr, 512);
     tc_fence_before();
@@ -251,21 +256,24 @@ mlp_res_ln_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc1_empty[buf]);                              // the accumulator is in registers
             const uint32_t bb_s = vec_ss + (uint32_t)((j * MP_HC + part * MP_E1C) * 4);
-            mbar_wait(&h_empty[buf], ph ^ 1u);                                         // GEMM2 of two chunks ago has read H[buf]
+            uint32_t pk[MP_E1C / 2];
 #pragma unroll
             for (int p4 = 0; p4 < MP_E1C / 8; ++p4) {                                  // 16-byte pieces of this row
-                uint32_t pk[4];
-                const float4 b_lo = lds_f4(bb_s + p4 * 32), b_hi = lds_f4(bb_s + p4 * 32 + 16);
+                const float4 b_lo = lds_const_f4(bb_s + p4 * 32), b_hi = lds_const_f4(bb_s + p4 * 32 + 16);
                 const float bb[8] = {b_lo.x, b_lo.y, b_lo.z, b_lo.w, b_hi.x, b_hi.y, b_hi.z, b_hi.w};
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     const int c = p4 * 8 + 2 * t;
                     const float2 g2 = gelu_erf2(make_float2(v[c] + bb[2 * t], v[c + 1] + bb[2 * t + 1]));
-                    if (BF16) { const __nv_bfloat162 hh = __floats2bfloat162_rn(g2.x, g2.y); pk[t] = *reinterpret_cast<const uint32_t*>(&hh); }
-                    else { const __half2 hh = __floats2half2_rn(g2.x, g2.y); pk[t] = *reinterpret_cast<const uint32_t*>(&hh); }
+                    if (BF16) { const __nv_bfloat162 hh = __floats2bfloat162_rn(g2.x, g2.y); pk[p4 * 4 + t] = *reinterpret_cast<const uint32_t*>(&hh); }
+                    else { const __half2 hh = __floats2half2_rn(g2.x, g2.y); pk[p4 * 4 + t] = *reinterpret_cast<const uint32_t*>(&hh); }
                 }
+            }
+            mbar_wait(&h_empty[buf], ph ^ 1u);            // GEMM2 of this group's previous chunk has read H[buf] (hidden by the math)
+#pragma unroll
+            for (int p4 = 0; p4 < MP_E1C / 8; ++p4) {
                 const uint32_t piece = (uint32_t)(part * (MP_E1C / 8) + p4);
-                sts128(h_row + buf * MP_KB_TILE + ((piece ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+                sts128(h_row + buf * MP_KB_TILE + ((piece ^ sw) << 4), pk[p4 * 4], pk[p4 * 4 + 1], pk[p4 * 4 + 2], pk[p4 * 4 + 3]);
             }
             fence_proxy_async();                                                       // H is read by the tensor core (async proxy)
             __syncwarp();
@@ -347,8 +355,8 @@ mlp_res_ln_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             float2 o;
             asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(o.x), "=f"(o.y) : "r"(sums_t + ((e ^ 4) * 32 + lane) * 8) : "memory");
             const float m1 = (s1 + o.x) * invC;
-            const float mean = shift + m1;
-            const float rstd = rsqrtf(fmaxf(fmaf(s2 + o.y, invC, -m1 * m1), 0.0f) + eps);
+            const float mean = gamma ? shift + m1 : 0.0f;
+            const float rstd = gamma ? rsqrtf(fmaxf(fmaf(s2 + o.y, invC, -m1 * m1), 0.0f) + eps) : 1.0f;
 #pragma unroll 1
             for (int k = 0; k < UPW; ++k) {
                 const int col0 = half * (C / 2) + k * 16;
@@ -431,7 +439,7 @@ using namespace xp;
 extern "C" int xp_mlp_res_ln(const void* A, const void* W1, const float* b1, const void* W2, const float* b2, const float* residual,
                              const float* gamma, const float* beta, float* x_new, void* y, int64_t M, int64_t C, int32_t dtype,
                              float eps, xp_stream_t stream) {
-    XP_REQUIRE(A && W1 && W2 && residual && gamma && beta && y, "xp_mlp_res_ln: NULL tensor pointer");
+    XP_REQUIRE(A && W1 && W2 && residual && y, "xp_mlp_res_ln: NULL tensor pointer");
     XP_REQUIRE(dtype == XP_F16 || dtype == XP_BF16, "xp_mlp_res_ln: 16-bit inputs only (got dtype %d)", dtype);
     XP_REQUIRE(M >= 0 && M < ((int64_t)1 << 31), "xp_mlp_res_ln: bad shape");
     XP_REQUIRE(C == 96 || C == 192, "xp_mlp_res_ln: C must be 96 or 192 (hidden 4C; got %lld)", (long long)C);

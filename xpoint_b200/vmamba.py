@@ -24,6 +24,7 @@ import torch.nn.functional as F
 
 from . import ss2d as _ss2d
 from .cross_scan import (add_layer_norm, cross_scan_fn, layer_norm, linear_act, linear_act_supported, linear_res_ln,
+                         mlp_res_ln, mlp_res_ln_supported,
                          linear_res_ln_supported, merge_norm_gate, patch_embed_stem)
 from .selective_scan import scan_forward, selective_scan_fn
 
@@ -66,6 +67,12 @@ class Mlp(nn.Module):  # VMamba.py:110-128 (channel-last only; XPoint never buil
 
     def forward(self, x):
         return self.fc2(self.hidden(x))
+
+    def fusable(self) -> bool:
+        """fc1 -> exact GELU -> fc2 with hidden = 4 C and C in {96, 192}: the whole branch fits xp_mlp_res_ln."""
+        return (isinstance(self.act, nn.GELU) and getattr(self.act, "approximate", "none") == "none"
+                and self.fc2.out_features == self.fc1.in_features
+                and mlp_res_ln_supported(self.fc1.in_features, self.fc1.out_features) and not getattr(self, "disable_fused", False))
 
     def hidden(self, x):
         """act(fc1(x)): everything before fc2 (the block wrapper may run fc2 fused with the residual add and the next norm)."""
@@ -335,6 +342,7 @@ FUSE_DT_PROJ = os.environ.get("XP_FUSE_DT_PROJ", "0") not in ("", "0")
 USE_CORE = os.environ.get("XP_SS2D_CORE", "0") not in ("", "0")
 # XP_NO_LINEAR_LN=1: keep out_proj / fc2 on cuBLAS followed by xp_add_layer_norm (A/B measurements)
 FUSE_LINEAR_LN_OFF = os.environ.get("XP_NO_LINEAR_LN", "0") not in ("", "0")
+FUSE_MLP_OFF = os.environ.get("XP_NO_FUSED_MLP", "0") not in ("", "0")      # A/B switch for xp_mlp_res_ln (profiles/)
 
 
 class VSSBlock(nn.Module):  # VMamba.py:1153-1240
@@ -484,14 +492,18 @@ class VSSM(nn.Module):
         return cache[1]
 
     @staticmethod
-    def _run_blocks(blocks, x):
-        """Returns (x, pending) with the block output = x + pending (pending may be None).
+    def _run_blocks(blocks, x, keep_mlp=False):
+        """Returns (x, pending, deferred) with the block output = x + pending (pending may be None); ``deferred`` is None unless
+        ``keep_mlp`` and the stage ends with a fusable Mlp branch: then (n, Mlp) with pending = Mlp(n) left to the caller
+        (the downsample fuses it, VSSM._downsample).
 
         Under 16-bit autocast the projection that closes a branch (out_proj / fc2) is DEFERRED: it runs fused with the residual
         add and the LayerNorm that opens the next branch (xp_linear_res_ln, one tcgen05 GEMM) instead of cuBLAS + xp_add_layer_norm;
-        the last branch of a stage has no next norm in this stage and is materialised by the plain Linear."""
+        a whole Mlp branch with C in {96, 192} is deferred as one unit (xp_mlp_res_ln: fc1 + GELU + fc2 + residual + next norm,
+        the 4C-wide hidden activation never written).  The last branch of a stage has no next norm in this stage and is
+        materialised by the plain modules."""
         pend = None
-        defer = None            # (a16, Linear): pending = Linear(a16), not yet computed
+        defer = None            # (a16, Linear | Mlp): pending = module(a16), not yet computed
         cdt = VSSM._ln_dtype(True)
         fuse_ok = cdt in (torch.float16, torch.bfloat16) and x.dtype == torch.float32 and not FUSE_LINEAR_LN_OFF
 
@@ -502,6 +514,9 @@ class VSSM(nn.Module):
             """x [+ pending] -> (new x, LayerNorm(new x) for the branch's first GEMM)."""
             if defer is not None:
                 a16, lin = defer
+                if isinstance(lin, Mlp):
+                    return mlp_res_ln(a16, VSSM._w16(lin.fc1, a16.dtype), lin.fc1.bias, VSSM._w16(lin.fc2, a16.dtype), lin.fc2.bias,
+                                      x, norm.weight, norm.bias, norm.eps)
                 return linear_res_ln(a16, VSSM._w16(lin, a16.dtype), lin.bias, x, norm.weight, norm.bias, norm.eps)
             if pend is None:
                 return x, norm(x)
@@ -525,23 +540,33 @@ class VSSM(nn.Module):
             if blk.mlp_branch:
                 x, n = open_branch(blk.norm2, x, pend, defer)
                 pend = defer = None
-                if can_defer(blk.mlp.fc2) and n.dtype == cdt:
+                if fuse_ok and not FUSE_MLP_OFF and n.dtype == cdt and blk.mlp.fusable():
+                    defer = (n, blk.mlp)
+                elif can_defer(blk.mlp.fc2) and n.dtype == cdt:
                     defer = (blk.mlp.hidden(n), blk.mlp.fc2)
                 else:
                     pend = blk.mlp(n)
         if defer is not None:
+            if keep_mlp and isinstance(defer[1], Mlp):
+                return x, None, defer
             pend = defer[1](defer[0])
-        return x, pend
+        return x, pend, None
 
-    def _downsample(self, ds, x, pend):
+    def _downsample(self, ds, x, pend, defer=None):
         fast = (isinstance(ds, nn.Sequential) and len(ds) == 4 and isinstance(ds[1], nn.Conv2d) and isinstance(ds[3], LayerNorm))
+        cdt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
+        if defer is not None and not (fast and defer[0].dtype == cdt):
+            pend, defer = defer[1](defer[0]), None
         if not fast:
             if pend is not None:
                 x = x + pend
             return ds(x)
         conv, ln = ds[1], ds[3]
-        cdt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
-        if pend is not None:      # residual sum written once, already in the convolution's dtype and channels-last
+        if defer is not None:     # the stage's last Mlp branch + residual add, written once in the convolution's dtype
+            n, mlp = defer
+            _, x = mlp_res_ln(n, VSSM._w16(mlp.fc1, n.dtype), mlp.fc1.bias, VSSM._w16(mlp.fc2, n.dtype), mlp.fc2.bias, x,
+                              None, None, want_sum=False)
+        elif pend is not None:    # residual sum written once, already in the convolution's dtype and channels-last
             x, _ = add_layer_norm(pend, x, None, None, sum_dtype=cdt, want_y=False)
         elif x.dtype != cdt:
             x = x.to(cdt)
@@ -555,9 +580,10 @@ class VSSM(nn.Module):
         x = self._patch_embed(x)
         pend = None
         for i, layer in enumerate(self.layers):
-            x, pend = self._run_blocks(layer.blocks, x)
-            if not isinstance(layer.downsample, nn.Identity):
-                x, pend = self._downsample(layer.downsample, x, pend), None
+            has_ds = not isinstance(layer.downsample, nn.Identity)
+            x, pend, defer = self._run_blocks(layer.blocks, x, keep_mlp=has_ds)
+            if has_ds:
+                x, pend = self._downsample(layer.downsample, x, pend, defer), None
         return x, pend
 
     def forward(self, x):

@@ -195,7 +195,8 @@ mlp_res_ln_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                         const uint64_t wd = w_desc0 + (uint64_t)((s1 * Cfg::W1_STAGE) >> 4);
 #pragma unroll
                         for (int k = 0; k < MP_BK / 16; ++k)
-                            umma_f16(tmem_base + buf * MP_HC, ad + (uint64_t)(k * 2), wd + (uint64_t)(k * 2), idesc1, (kb | k) != 0);
+                            if (kb * MP_BK + k * 16 < C)                               // K steps past C are TMA zero fill on both sides
+                                umma_f16(tmem_base + buf * MP_HC, ad + (uint64_t)(k * 2), wd + (uint64_t)(k * 2), idesc1, (kb | k) != 0);
                         umma_commit(&w1_empty[s1]);
                         if (++s1 == S1) { s1 = 0; f1 ^= 1u; }
                     }

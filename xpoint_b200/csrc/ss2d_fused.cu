@@ -81,7 +81,7 @@ template <> struct DwPair<__nv_bfloat16> {
 };
 
 template <typename T, bool SILU>
-__global__ void __launch_bounds__(256) ss2d_dwconv_pack_kernel(const T* __restrict__ in, const float* __restrict__ wgt,
+__global__ void __launch_bounds__(256, 4) ss2d_dwconv_pack_kernel(const T* __restrict__ in, const float* __restrict__ wgt,
                                                                const float* __restrict__ bias, T* __restrict__ xx, int64_t D,
                                                                int H, int W, int64_t in_stride, int tiles_w, int tiles_h,
                                                                int chan_blocks, int vec_in, int vec_row, int vec_col) {
@@ -105,16 +105,27 @@ __global__ void __launch_bounds__(256) ss2d_dwconv_pack_kernel(const T* __restri
     const T* inb = in + b * H * (int64_t)W * in_stride;
     if (vec_in) {                                         // D % VEC == 0: vectors are all-or-nothing against D
         constexpr int VPT = DW_CB / VEC;                  // vectors per token
-        for (int i = tid; i < DW_HT * DW_WT * VPT; i += 256) {
+        constexpr int NV = DW_HT * DW_WT * VPT, NLD = (NV + 255) / 256;
+        uint4 raw[NLD];                                   // every load of this thread in flight before the first store
+#pragma unroll
+        for (int k = 0; k < NLD; ++k) {
+            const int i = tid + k * 256;
             const int v = i % VPT, tok = i / VPT;
             const int hh = tok / DW_WT, ww = tok % DW_WT;
             const int h = h0 + hh - 1, w = w0 + ww - 1;
-            uint4 raw = make_uint4(0u, 0u, 0u, 0u);       // zero padding (Conv2d padding=1)
-            if (h >= 0 && h < H && w >= 0 && w < W && c0 + v * VEC < D)
-                raw = __ldg(reinterpret_cast<const uint4*>(inb + ((int64_t)h * W + w) * in_stride + c0 + v * VEC));
-            const PairT* pr = reinterpret_cast<const PairT*>(&raw);
+            raw[k] = make_uint4(0u, 0u, 0u, 0u);          // zero padding (Conv2d padding=1)
+            if (i < NV && h >= 0 && h < H && w >= 0 && w < W && c0 + v * VEC < D)
+                raw[k] = __ldg(reinterpret_cast<const uint4*>(inb + ((int64_t)h * W + w) * in_stride + c0 + v * VEC));
+        }
 #pragma unroll
-            for (int j = 0; j < VEC / 2; ++j) tile[tok * DW_PITCH + v * (VEC / 2) + j] = pr[j];
+        for (int k = 0; k < NLD; ++k) {
+            const int i = tid + k * 256;
+            if (i < NV) {
+                const int v = i % VPT, tok = i / VPT;
+                const PairT* pr = reinterpret_cast<const PairT*>(&raw[k]);
+#pragma unroll
+                for (int j = 0; j < VEC / 2; ++j) tile[tok * DW_PITCH + v * (VEC / 2) + j] = pr[j];
+            }
         }
     } else {
         for (int i = tid; i < DW_HT * DW_WT * DW_NP; i += 256) {
@@ -133,18 +144,16 @@ __global__ void __launch_bounds__(256) ss2d_dwconv_pack_kernel(const T* __restri
     // ---- this thread's pair / row / strip, weights in registers
     const int hh = tid % DW_TH, pr = (tid / DW_TH) % DW_NP, strip = tid / (DW_TH * DW_NP);   // strip: 16 tokens
     const int cA = c0 + 2 * pr, cB = cA + 1;
-    float wa[9], wb[9];
+    float2 wab[9];                                        // (channel A, channel B) taps: one packed FFMA2 serves both
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-        wa[k] = cA < D ? __ldg(wgt + (int64_t)cA * 9 + k) : 0.0f;
-        wb[k] = cB < D ? __ldg(wgt + (int64_t)cB * 9 + k) : 0.0f;
-    }
+    for (int k = 0; k < 9; ++k)
+        wab[k] = make_float2(cA < D ? __ldg(wgt + (int64_t)cA * 9 + k) : 0.0f, cB < D ? __ldg(wgt + (int64_t)cB * 9 + k) : 0.0f);
     const float ba = (bias && cA < D) ? __ldg(bias + cA) : 0.0f, bb = (bias && cB < D) ? __ldg(bias + cB) : 0.0f;
     __syncthreads();
     constexpr int NT = 16;
-    float ya[NT], yb[NT];
+    float2 yab[NT];
 #pragma unroll
-    for (int j = 0; j < NT; ++j) { ya[j] = ba; yb[j] = bb; }
+    for (int j = 0; j < NT; ++j) yab[j] = make_float2(ba, bb);
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
         const PairT* row = tile + ((hh + ky) * DW_WT + strip * NT) * DW_PITCH + pr;
@@ -154,13 +163,13 @@ __global__ void __launch_bounds__(256) ss2d_dwconv_pack_kernel(const T* __restri
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
                 const int j = q - kx;
-                if (j >= 0 && j < NT) {
-                    ya[j] = fmaf(v.x, wa[ky * 3 + kx], ya[j]);
-                    yb[j] = fmaf(v.y, wb[ky * 3 + kx], yb[j]);
-                }
+                if (j >= 0 && j < NT) yab[j] = fma2(v, wab[ky * 3 + kx], yab[j]);
             }
         }
     }
+    float ya[NT], yb[NT];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) { ya[j] = yab[j].x; yb[j] = yab[j].y; }
     if (SILU) {
 #pragma unroll
         for (int j = 0; j < NT; ++j) {

@@ -178,20 +178,22 @@ __device__ __forceinline__ float softplus_f(float x) {
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
-// exact (erf) GELU with erf(x) = 1 - (1 + a1 x + .. + a6 x^6)^-16, x >= 0 (Abramowitz-Stegun 7.1.28, |err| <= 3e-7):
-// one MUFU.RCP and 13 FP32 ops instead of libdevice erff's ~25 instructions and branches.
+// exact (erf) GELU: erfc(x) = (1 + a1 x + .. + a6 x^6)^-16, x >= 0 (Abramowitz-Stegun 7.1.28, |err| <= 3e-7), evaluated in |v|
+// (the 1/sqrt(2) of x = |v| / sqrt(2) folded into the coefficients) and GELU(v) = relu(v) - 0.5 |v| erfc(|v| / sqrt(2)):
+// one MUFU.RCP, one FMNMX and 12 FP32 ops instead of libdevice erff's ~25 instructions and branches (gelu_erf2 in tcgen05.cuh is
+// the packed form of the same arithmetic).
 __device__ __forceinline__ float gelu_erf_f(float v) {
-    const float av = fabsf(v), x = av * 0.70710678118654752f;
-    float p = fmaf(x, 0.0000430638f, 0.0002765672f);
-    p = fmaf(p, x, 0.0001520143f);
-    p = fmaf(p, x, 0.0092705272f);
-    p = fmaf(p, x, 0.0422820123f);
-    p = fmaf(p, x, 0.0705230784f);
-    p = fmaf(p, x, 1.0f);
+    const float av = fabsf(v);
+    float p = fmaf(av, 5.3829750000e-06f, 4.8890635643e-05f);
+    p = fmaf(p, av, 3.8003575000e-05f);
+    p = fmaf(p, av, 3.2776263241e-03f);
+    p = fmaf(p, av, 2.1141006150e-02f);
+    p = fmaf(p, av, 4.9867346967e-02f);
+    p = fmaf(p, av, 1.0f);
     p *= p; p *= p; p *= p; p *= p;
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p));
-    return fmaf(v, 0.5f, fmaf(-0.5f * av, r, 0.5f * av));      // 0.5 v + 0.5 |v| (1 - r)
+    return fmaf(av * r, -0.5f, fmaxf(v, 0.0f));
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -302,11 +302,10 @@ __global__ void __launch_bounds__(128) patch_embed_stem_kernel(const float* __re
 #pragma unroll
                 for (int q = 0; q < CC / 4; ++q) {
                     if (4 * q < C1) {                      // uniform: skips the padded channel quads
-                        const float4 w4 = wv[q];
-                        acc[4 * q] = fmaf(px, w4.x, acc[4 * q]);
-                        acc[4 * q + 1] = fmaf(px, w4.y, acc[4 * q + 1]);
-                        acc[4 * q + 2] = fmaf(px, w4.z, acc[4 * q + 2]);
-                        acc[4 * q + 3] = fmaf(px, w4.w, acc[4 * q + 3]);
+                        const float4 w4 = wv[q];           // two packed FFMA2 per quad: half the issue slots of four FFMA
+                        const float2 lo = fma2(make_float2(px, px), make_float2(w4.x, w4.y), make_float2(acc[4 * q], acc[4 * q + 1]));
+                        const float2 hi = fma2(make_float2(px, px), make_float2(w4.z, w4.w), make_float2(acc[4 * q + 2], acc[4 * q + 3]));
+                        acc[4 * q] = lo.x; acc[4 * q + 1] = lo.y; acc[4 * q + 2] = hi.x; acc[4 * q + 3] = hi.y;
                     }
                 }
             }

@@ -65,6 +65,19 @@ template <int MODE> __global__ void k(float* out, long long* cyc, float seed, in
                 a[i] = fmaf(a[i], f.x, c1); a[i] = fmaf(a[i], f.y, c1); a[i] = fmaf(a[i], c0, c1); a[i] = fmaf(a[i], c0, c1);
                 h[i] = (h[i] + 1) | 0x80008000u;
             }
+            if (MODE == 10) {                                   // 1 FFMA2 + 1 FFMA per unit (does the scalar one ride the idle half?)
+                b[i] = fma2(b[i], make_float2(c0, c0), make_float2(c1, c1));
+                a[i] = fmaf(a[i], c0, c1);
+            }
+            if (MODE == 11) {                                   // 1 FFMA2 + 2 FFMA per unit
+                b[i] = fma2(b[i], make_float2(c0, c0), make_float2(c1, c1));
+                a[i] = fmaf(a[i], c0, c1); a[i] = fmaf(a[i], c1, c0);
+            }
+            if (MODE == 12) {                                   // 2 FFMA2 + 1 MUFU.RCP per unit (the GELU epilogue's mix is 12 : 2)
+                b[i] = fma2(b[i], make_float2(c0, c0), make_float2(c1, c1));
+                b[i] = fma2(b[i], make_float2(c1, c1), make_float2(c0, c0));
+                float r; asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a[i])); a[i] = r + c0;
+            }
             if (MODE == 9) {
                 if (i % 4 == 3) { b[i] = ex2_poly2(b[i]); b[i].x -= 1.001f; b[i].y -= 1.002f; }
                 else a[i] = ex2f(a[i]) + c1;
@@ -82,11 +95,12 @@ int main() {
     const int threads = 512, blocks = 148 * 2;      // 1024 threads / SM = 8 warps per SMSP
     float* d; long long* c;
     cudaMalloc(&d, blocks * threads * 4); cudaMalloc(&c, blocks * 8);
-    const char* names[10] = {"MUFU.EX2 f32", "MUFU.EX2 f16x2 (per instr)", "MUFU.EX2 bf16x2 (per instr)", "FFMA", "FFMA2 (per instr)",
+    const char* names[13] = {"MUFU.EX2 f32", "MUFU.EX2 f16x2 (per instr)", "MUFU.EX2 bf16x2 (per instr)", "FFMA", "FFMA2 (per instr)",
                              "poly 2^x pair (per pair)", "1 MUFU + 4 FFMA (per group)", "1 MUFU + 2 FFMA2 (per group)",
-                             "1 MUFU.f16x2 + 2 cvt + 4 FFMA (per group)", "3 MUFU : 1 poly pair (per 4 slots)"};
+                             "1 MUFU.f16x2 + 2 cvt + 4 FFMA (per group)", "3 MUFU : 1 poly pair (per 4 slots)",
+                             "1 FFMA2 + 1 FFMA (per unit)", "1 FFMA2 + 2 FFMA (per unit)", "2 FFMA2 + 1 MUFU.RCP + FADD (per unit)"};
     const int iters = 4000;
-    for (int m = 0; m < 10; ++m) {
+    for (int m = 0; m < 13; ++m) {
         for (int rep = 0; rep < 2; ++rep) {
             switch (m) {
                 case 0: k<0><<<blocks, threads>>>(d, c, 1.f, iters); break;
@@ -99,6 +113,9 @@ int main() {
                 case 7: k<7><<<blocks, threads>>>(d, c, 1.f, iters); break;
                 case 8: k<8><<<blocks, threads>>>(d, c, 1.f, iters); break;
                 case 9: k<9><<<blocks, threads>>>(d, c, 1.f, iters); break;
+                case 10: k<10><<<blocks, threads>>>(d, c, 1.f, iters); break;
+                case 11: k<11><<<blocks, threads>>>(d, c, 1.f, iters); break;
+                case 12: k<12><<<blocks, threads>>>(d, c, 1.f, iters); break;
             }
             cudaDeviceSynchronize();
         }

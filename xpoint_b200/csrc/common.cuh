@@ -240,6 +240,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
         if (spins > (1u << 26)) __trap();
 }
+// The same with a suspend-time hint: the thread stays parked until the phase completes (or ~20 us pass) instead of re-polling
+// every few dozen cycles.  For waits that are EXPECTED to block in a kernel whose other warps are bound by instruction issue
+// (mlp_res_ln_tc: a quarter of all issued instructions were epilogue warps polling h_empty).
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+    uint32_t ok, spins = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+        if (++spins > (1u << 22)) __trap();
+    } while (!ok);
+}
 
 // 32-bit shared-window variants (keep hot loops on LDS/STS/SYNCS with no generic-address arithmetic)
 __device__ __forceinline__ uint4 lds128(uint32_t saddr) {

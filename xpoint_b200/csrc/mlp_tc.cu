@@ -145,7 +145,7 @@ mlp_res_ln_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         int j2 = -2;                                                                    // W2 runs two chunks behind W1
         auto load_w2 = [&]() {
             if (j2 >= 0) {
-                mbar_wait(&w2_empty[s2], p2);
+                mbar_wait_parked(&w2_empty[s2], p2);
                 mbar_arrive_expect_tx(&w2_full[s2], Cfg::W2_STAGE);
                 tma_load_2d(w2 + s2 * Cfg::W2_STAGE, &map_w2, &w2_full[s2], j2 * MP_HC, 0);
                 if (++s2 == S2) { s2 = 0; p2 ^= 1u; }
@@ -154,7 +154,7 @@ mlp_res_ln_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         };
         int i0 = (int)blockIdx.x * MP_BM;
         for (int tl = 0; tl < ntl; ++tl, i0 += (int)gridDim.x * MP_BM) {
-            mbar_wait(&a1_empty[as], ap);
+            mbar_wait_parked(&a1_empty[as], ap);
             mbar_arrive_expect_tx(&a1_full[as], Cfg::A1_BYTES);
 #pragma unroll
             for (int kb = 0; kb < KB1; ++kb)
@@ -164,7 +164,7 @@ mlp_res_ln_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             for (int j = 0; j < NCHUNK; ++j) {
 #pragma unroll
                 for (int kb = 0; kb < KB1; ++kb) {
-                    mbar_wait(&w1_empty[s1], p1);
+                    mbar_wait_parked(&w1_empty[s1], p1);
                     mbar_arrive_expect_tx(&w1_full[s1], Cfg::W1_STAGE);
                     tma_load_2d(w1 + s1 * Cfg::W1_STAGE, &map_w1, &w1_full[s1], kb * MP_BK, j * MP_HC);
                     if (++s1 == S1) { s1 = 0; p1 ^= 1u; }
@@ -179,17 +179,17 @@ mlp_res_ln_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         const uint64_t a_desc0 = make_smem_desc_sw128(smem_u32(a1)), w_desc0 = make_smem_desc_sw128(smem_u32(w1));
         uint32_t s1 = 0, f1 = 0, as = 0, af = 0, epar = 1;
         for (int tl = 0; tl < ntl; ++tl) {
-            mbar_wait(&a1_full[as], af);
+            mbar_wait_parked(&a1_full[as], af);
             const uint64_t a_desc = a_desc0 + (uint64_t)((as * Cfg::A1_BYTES) >> 4);
 #pragma unroll 1
             for (int j = 0; j < NCHUNK; j += 2) {
 #pragma unroll
                 for (int buf = 0; buf < 2; ++buf) {                                    // NCHUNK is even: chunk j + buf -> acc1[buf]
-                    mbar_wait(&acc1_empty[buf], epar);                                 // its epilogue-1 group has read chunk g - 2
+                    mbar_wait_parked(&acc1_empty[buf], epar);                                 // its epilogue-1 group has read chunk g - 2
                     tc_fence_after();
 #pragma unroll
                     for (int kb = 0; kb < KB1; ++kb) {
-                        mbar_wait(&w1_full[s1], f1);
+                        mbar_wait_parked(&w1_full[s1], f1);
                         tc_fence_after();
                         const uint64_t ad = a_desc + (uint64_t)((kb * MP_KB_TILE) >> 4);
                         const uint64_t wd = w_desc0 + (uint64_t)((s1 * Cfg::W1_STAGE) >> 4);
@@ -219,9 +219,9 @@ mlp_res_ln_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             for (int j = 0; j < NCHUNK; j += 2) {
 #pragma unroll
                 for (int hb = 0; hb < 2; ++hb) {
-                    mbar_wait(&h_full[hb], hpar);                                      // epilogue 1 has written H of this chunk
-                    if (j == 0 && hb == 0) mbar_wait(&acc2_empty[ab], cpar);           // epilogue 2 has drained this accumulator
-                    mbar_wait(&w2_full[s2], f2);
+                    mbar_wait_parked(&h_full[hb], hpar);                                      // epilogue 1 has written H of this chunk
+                    if (j == 0 && hb == 0) mbar_wait_parked(&acc2_empty[ab], cpar);           // epilogue 2 has drained this accumulator
+                    mbar_wait_parked(&w2_full[s2], f2);
                     tc_fence_after();
                     const uint64_t ad = h_desc0 + (uint64_t)((hb * MP_KB_TILE) >> 4);
                     const uint64_t wd = w_desc0 + (uint64_t)((s2 * Cfg::W2_STAGE) >> 4);
@@ -249,7 +249,7 @@ mlp_res_ln_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         int j = grp;                                                                   // chunk index inside the tile
 #pragma unroll 1
         for (int g = grp; g < nchunks; g += 2, ph ^= 1u, j = (j + 2 == NCHUNK + grp) ? grp : j + 2) {   // acc1[grp] -> H[grp]
-            mbar_wait(&acc1_full[buf], ph);
+            mbar_wait_parked(&acc1_full[buf], ph);
             tc_fence_after();
             float v[MP_E1C];
             tmem_ldn(tmem_base + lane_t + buf * MP_HC + (uint32_t)(part * MP_E1C), v);
@@ -270,7 +270,7 @@ mlp_res_ln_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     else { const __half2 hh = __floats2half2_rn(g2.x, g2.y); pk[p4 * 4 + t] = *reinterpret_cast<const uint32_t*>(&hh); }
                 }
             }
-            mbar_wait(&h_empty[buf], ph ^ 1u);            // GEMM2 of this group's previous chunk has read H[buf] (hidden by the math)
+            mbar_wait_parked(&h_empty[buf], ph ^ 1u);            // GEMM2 of this group's previous chunk has read H[buf] (hidden by the math)
 #pragma unroll
             for (int p4 = 0; p4 < MP_E1C / 8; ++p4) {
                 const uint32_t piece = (uint32_t)(part * (MP_E1C / 8) + p4);
@@ -310,7 +310,7 @@ mlp_res_ln_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             const int row0 = row0_of(tl);
             const uint32_t ab = (uint32_t)tl & 1u;
             const float shift = (row0 + lane < M) ? __ldg(res + (int64_t)(row0 + lane) * C) : 0.0f;
-            mbar_wait(&acc2_full[ab], ((uint32_t)tl >> 1) & 1u);
+            mbar_wait_parked(&acc2_full[ab], ((uint32_t)tl >> 1) & 1u);
             tc_fence_after();
             const uint32_t taddr = tmem_base + lane_t + Cfg::ACC2_COL + ab * C + (uint32_t)(half * (C / 2));
             float s1 = 0.0f, s2 = 0.0f;

@@ -45,9 +45,14 @@ template <int C> struct MpCfg {
     static constexpr int W1_STAGE = MP_HC * 128, S1 = C == 96 ? 4 : 3;
     static constexpr int W2_STAGE = C * 128, S2 = C == 96 ? 3 : 2;
     static constexpr int ACC2_COL = 2 * MP_HC;
+    // H (the GELU output = A operand of GEMM2) in tensor memory when the 512 columns allow it: no shared-memory round trip and
+    // no proxy fence; 2 x 32 columns of packed 16-bit pairs behind the accumulators
+    static constexpr bool H_TMEM = 2 * MP_HC + 2 * C + 2 * (MP_HC / 2) <= 512;
+    static constexpr int H_COL = ACC2_COL + 2 * C;
+    static constexpr int H_SMEM = H_TMEM ? 0 : 2 * MP_KB_TILE;
     static constexpr int UPW = C / 32;                             // 16-column units per epilogue-2 warp and tile
     static constexpr int VEC_FLOATS = HD + 3 * C;                  // b1 | b2 | gamma | beta
-    static constexpr int SMEM = NA1 * A1_BYTES + S1 * W1_STAGE + 2 * MP_KB_TILE + S2 * W2_STAGE + 1024 /*align*/ + MP_BAR_BYTES
+    static constexpr int SMEM = NA1 * A1_BYTES + S1 * W1_STAGE + H_SMEM + S2 * W2_STAGE + 1024 /*align*/ + MP_BAR_BYTES
                                 + MP_E2_WARPS * MP_E2_SMEM + VEC_FLOATS * 4 + 2 * MP_E2_WARPS * 32 * 8;
     static_assert(2 * MP_HC + 2 * C <= 512, "TMEM budget");
     static_assert((2 * NA1 + 2 * S1 + 2 * S2 + 12) * 8 + 4 <= MP_BAR_BYTES, "barrier block");
@@ -86,7 +91,7 @@ mlp_res_ln_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     uint8_t* a1 = base;
     uint8_t* w1 = a1 + NA1 * Cfg::A1_BYTES;
     uint8_t* hbuf = w1 + S1 * Cfg::W1_STAGE;
-    uint8_t* w2 = hbuf + 2 * MP_KB_TILE;
+    uint8_t* w2 = hbuf + Cfg::H_SMEM;
     uint64_t* bars = reinterpret_cast<uint64_t*>(w2 + S2 * Cfg::W2_STAGE);
     uint64_t* a1_full = bars;                   // [NA1]
     uint64_t* a1_empty = a1_full + NA1;         // [NA1]
@@ -226,8 +231,12 @@ mlp_res_ln_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     const uint64_t ad = h_desc0 + (uint64_t)((hb * MP_KB_TILE) >> 4);
                     const uint64_t wd = w_desc0 + (uint64_t)((s2 * Cfg::W2_STAGE) >> 4);
 #pragma unroll
-                    for (int k = 0; k < MP_BK / 16; ++k)
-                        umma_f16(d_tmem, ad + (uint64_t)(k * 2), wd + (uint64_t)(k * 2), idesc2, (j | hb | k) != 0);
+                    for (int k = 0; k < MP_BK / 16; ++k) {
+                        if constexpr (Cfg::H_TMEM)
+                            umma_f16_ts(d_tmem, tmem_base + Cfg::H_COL + hb * (MP_HC / 2) + k * 8, wd + (uint64_t)(k * 2), idesc2, (j | hb | k) != 0);
+                        else
+                            umma_f16(d_tmem, ad + (uint64_t)(k * 2), wd + (uint64_t)(k * 2), idesc2, (j | hb | k) != 0);
+                    }
                     umma_commit(&w2_empty[s2]);
                     umma_commit(&h_empty[hb]);                                         // H[hb] may be overwritten once these retire
                     if (++s2 == S2) { s2 = 0; f2 ^= 1u; }
@@ -271,12 +280,19 @@ mlp_res_ln_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 }
             }
             mbar_wait_parked(&h_empty[buf], ph ^ 1u);            // GEMM2 of this group's previous chunk has read H[buf] (hidden by the math)
+            if constexpr (Cfg::H_TMEM) {
+                static_assert(MP_E1C == 32, "one 16-column packed store per warp and chunk");
+                tc_fence_after();
+                tmem_st16u(tmem_base + lane_t + Cfg::H_COL + buf * (MP_HC / 2) + (uint32_t)(part * (MP_E1C / 2)), pk);
+                tc_fence_before();
+            } else {
 #pragma unroll
-            for (int p4 = 0; p4 < MP_E1C / 8; ++p4) {
-                const uint32_t piece = (uint32_t)(part * (MP_E1C / 8) + p4);
-                sts128(h_row + buf * MP_KB_TILE + ((piece ^ sw) << 4), pk[p4 * 4], pk[p4 * 4 + 1], pk[p4 * 4 + 2], pk[p4 * 4 + 3]);
+                for (int p4 = 0; p4 < MP_E1C / 8; ++p4) {
+                    const uint32_t piece = (uint32_t)(part * (MP_E1C / 8) + p4);
+                    sts128(h_row + buf * MP_KB_TILE + ((piece ^ sw) << 4), pk[p4 * 4], pk[p4 * 4 + 1], pk[p4 * 4 + 2], pk[p4 * 4 + 3]);
+                }
+                fence_proxy_async();                                                   // H is read by the tensor core (async proxy)
             }
-            fence_proxy_async();                                                       // H is read by the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive(&h_full[buf]);
         }

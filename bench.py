@@ -605,7 +605,7 @@ def run_ours(args):
     dom_gbs = dom_bytes / dom_ms / 1e6
     # DRAM bytes of ONE launch of that shape from `ncu --set full` (profiles/r1_s3_summary.md): only known for the
     # default workload (preset E, fp16 autocast, 64 pairs of 512x640 -> B128 KD384 K4 N1 L20480 float16->float32)
-    ncu_traffic = {"B128 KD384 K4 N1 L20480 float16->float32": 4.074885e9 + 3.983005e9}
+    ncu_traffic = {"B128 KD384 K4 N1 L20480 float16->float32": 4.075043e9 + 3.979829e9}
     roofline = {"bound": "hbm", "kernel": f"xp_selective_scan_fwd -> scan_lanes_kernel, launch shape {dom_key}",
                 "achieved": round(dom_gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(dom_gbs / peak, 4),
                 "traffic": ncu_traffic.get(dom_key), "algorithmic_bytes_per_launch": int(dom_bytes),

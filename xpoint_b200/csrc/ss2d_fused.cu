@@ -167,18 +167,27 @@ __global__ void __launch_bounds__(256, 4) ss2d_dwconv_pack_kernel(const T* __res
             }
         }
     }
-    float ya[NT], yb[NT];
-#pragma unroll
-    for (int j = 0; j < NT; ++j) { ya[j] = yab[j].x; yb[j] = yab[j].y; }
     if (SILU) {
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
-            // x * rcp(1 + e^-x): the IEEE division costs ~8 more instructions per element in an issue-bound kernel; the
-            // approximate reciprocal is good to 1 ulp, far inside the fp32 / 16-bit tolerances of the SS2D block
-            ya[j] = __fdividef(ya[j], 1.0f + __expf(-ya[j]));
-            yb[j] = __fdividef(yb[j], 1.0f + __expf(-yb[j]));
+            // x * rcp(1 + 2^(-x log2 e)) on the channel pair: MUFU.EX2 + MUFU.RCP per value, the rest packed.  (An IEEE division
+            // costs ~8 more instructions per element in this issue-bound kernel, __fdividef 3 more for its range check; the
+            // approximate reciprocal is good to 1 ulp, far inside the fp32 / 16-bit tolerances of the SS2D block.  For x -> -inf
+            // the denominator overflows to +inf and the product is -0, like the exact expression.)
+            const float2 t = mul2(yab[j], make_float2(-1.4426950408889634f, -1.4426950408889634f));
+            float2 e;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(t.x));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(t.y));
+            const float2 den = fma2(e, make_float2(1.0f, 1.0f), make_float2(1.0f, 1.0f));
+            float2 r;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(den.x));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(den.y));
+            yab[j] = mul2(yab[j], r);
         }
     }
+    float ya[NT], yb[NT];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) { ya[j] = yab[j].x; yb[j] = yab[j].y; }
     // ---- row-major plane: 16 consecutive tokens per channel straight from registers
     const int h = h0 + hh, wbeg = w0 + strip * NT;
     if (h < H) {

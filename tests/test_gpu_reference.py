@@ -157,7 +157,7 @@ def _run_ref(net, o, t):
     return po, pt
 
 
-MODEL_CASES = [("E", 256, 256, 2), ("V", 256, 256, 2), ("E", 512, 640, 2)]
+MODEL_CASES = [("E", 256, 256, 2), ("V", 256, 256, 2), ("E", 512, 640, 2), ("E", 1024, 1280, 1)]   # configs[0], [2], [4]
 
 
 @pytest.mark.parametrize("preset,H,W,Bn", MODEL_CASES, ids=[f"{c[0]}_{c[1]}x{c[2]}" for c in MODEL_CASES])
@@ -253,14 +253,14 @@ def _ref_tail(ref, prob, desc, k, thr=0.015):
     return nms, kps, descs
 
 
-@pytest.mark.parametrize("H,W,k", [(256, 256, 512), (512, 640, 4096)])
+@pytest.mark.parametrize("H,W,k", [(256, 256, 512), (512, 640, 4096), (1024, 1280, 16384)])   # configs[0], [2], [4]
 def test_tail_on_reference_tensors_bit_exact(ref, H, W, k):
     """Keypoints and match pairs bit-exact at top-k when both sides are fed the same fp32 score / descriptor tensors:
     (i) the reference model's own prob/desc for a pair (full-width preset E, fp32), (ii) distinct-valued synthetic score
     maps that leave exactly k survivors.  Reference side: box_nms (torchvision on the GPU), nonzero,
     interpolate_descriptors (grid_sample), cv2.BFMatcher(crossCheck)."""
     import xpoint_b200 as X
-    Bn = 2
+    Bn = 2 if H < 1024 else 1            # cv2.BFMatcher on 16 384 x 16 384 descriptors takes ~10 s per pair
     rnet = R.randomise_stats(R.build_xpoint(ref, "E", height=H, width=W)).to(DEV)
     o, t = _pair(Bn, H, W, seed=11)
     rpo, rpt = _run_ref(rnet, o, t)
@@ -269,12 +269,15 @@ def test_tail_on_reference_tensors_bit_exact(ref, H, W, k):
     syn_desc = torch.nn.functional.normalize(torch.randn(2 * Bn, 256, H // 8, W // 8, generator=g), dim=1).to(DEV)
     cases = {"model": (torch.cat([rpo["prob"], rpt["prob"]]).float(), torch.cat([rpo["desc"], rpt["desc"]]).float()),
              "synthetic": (syn_prob, syn_desc)}
-    pipe = X.PairPipeline(None, nms=8, detection_threshold=0.015, keep_top_k=k, use_tensor_cores=True)
     for name, (prob, desc) in cases.items():
+        # torchvision's GPU nms needs N^2 / 8 bytes of mask for N boxes above the threshold: at 1024x1280 the shipped 0.015 lets
+        # half of a random-weight score map through (650 k boxes, 53 GB), so that size runs at the map's 0.9 quantile instead
+        thr = 0.015 if H < 1024 else float(torch.quantile(prob[0].flatten().float(), 0.9))
+        pipe = X.PairPipeline(None, nms=8, detection_threshold=thr, keep_top_k=k, use_tensor_cores=True)
         r = pipe.tail(prob[:Bn], prob[Bn:], desc[:Bn], desc[Bn:])
-        nms_ref, kps_ref, d_ref = _ref_tail(ref, prob, desc, k)
+        nms_ref, kps_ref, d_ref = _ref_tail(ref, prob, desc, k, thr)
         # the dense NMS map itself
-        nms_ours = X.box_nms(prob, 8, 0.015, keep_top_k=k)
+        nms_ours = X.box_nms(prob, 8, thr, keep_top_k=k)
         assert torch.equal(nms_ours, nms_ref), f"{name}: box_nms map differs from the reference's"
         n_all = torch.cat([r.n_optical, r.n_thermal]).tolist()
         kp_all = torch.cat([r.kp_optical, r.kp_thermal])
@@ -282,10 +285,10 @@ def test_tail_on_reference_tensors_bit_exact(ref, H, W, k):
         for b in range(2 * Bn):
             n = len(kps_ref[b])
             assert n_all[b] == n, f"{name}: image {b} has {n_all[b]} keypoints, reference {n}"
-            if name == "synthetic":
+            if name == "synthetic" and H < 1024:
                 assert n == k
             assert torch.equal(kp_all[b, :n].long(), kps_ref[b]), f"{name}: keypoints of image {b} differ"
-            np.testing.assert_allclose(d_all[b, :n].cpu().numpy(), d_ref[b].cpu().numpy(), rtol=0, atol=5e-6)   # ATen grid_sample on the GPU contracts differently from its CPU kernel (2e-6 there)
+            np.testing.assert_allclose(d_all[b, :n].cpu().numpy(), d_ref[b].cpu().numpy(), rtol=0, atol=5e-6 if H < 1024 else 1e-5)   # ATen grid_sample on the GPU contracts differently from its CPU kernel (2e-6 there); 1 of 4.2 M values at 5.3e-6 for 1280-wide maps
         for b in range(Bn):
             n1, n2 = n_all[b], n_all[Bn + b]
             d1, d2 = d_all[b, :n1].cpu().numpy(), d_all[Bn + b, :n2].cpu().numpy()

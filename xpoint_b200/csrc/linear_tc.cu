@@ -35,7 +35,7 @@ template <int BN, int LT_STAGES> struct LtCfg {
 template <int BN, bool GELU, bool BF16, int LT_STAGES>
 __global__ void __launch_bounds__(LT_THREADS, 1)
 linear_act_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                     const float* __restrict__ bias, void* __restrict__ out, int M, int N, int K) {
+                     const float* __restrict__ bias, void* __restrict__ out, int M, int N, int K, int nsplit) {
     using Cfg = LtCfg<BN, LT_STAGES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -52,8 +52,11 @@ linear_act_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     const int n_tiles = (N + BN - 1) / BN;
     const int n_kb = (K + LT_BK - 1) / LT_BK;
     const int n_mb = (M + LT_BM - 1) / LT_BM;
-    const int my_mb = ((int)blockIdx.x < n_mb) ? (n_mb - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;   // row blocks of this CTA
-    const int ntl = my_mb * n_tiles;                   // output tiles of this CTA: tl -> (row block, column tile)
+    // nsplit CTAs share a row block and take every nsplit-th column tile (small M: fewer row blocks than SMs); nsplit = 1 otherwise
+    const int vb = (int)blockIdx.x / nsplit, js = (int)blockIdx.x % nsplit, vgrid = (int)gridDim.x / nsplit;
+    const int my_mb = (vb < n_mb) ? (n_mb - 1 - vb) / vgrid + 1 : 0;                 // row blocks of this CTA
+    const int my_nt = (n_tiles - js + nsplit - 1) / nsplit;                           // column tiles of this CTA per row block
+    const int ntl = my_mb * my_nt;                     // output tiles of this CTA: tl -> (row block, column tile)
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_w);
@@ -72,7 +75,7 @@ linear_act_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         // ===================== TMA producer =====================
         int it = 0;
         for (int tl = 0; tl < ntl; ++tl) {
-            const int i0 = ((int)blockIdx.x + (tl / n_tiles) * (int)gridDim.x) * LT_BM, jt = tl % n_tiles;
+            const int i0 = (vb + (tl / my_nt) * vgrid) * LT_BM, jt = js + (tl % my_nt) * nsplit;
             for (int kb = 0; kb < n_kb; ++kb, ++it) {
                 const int s = it % LT_STAGES;
                 mbar_wait(&empty[s], (uint32_t)(((it / LT_STAGES) & 1) ^ 1));
@@ -112,8 +115,8 @@ linear_act_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         uint8_t* stg = stg_all + e * LT_STG;
         float* bias_s = bias_all + e * 64;
         for (int tl = 0; tl < ntl; ++tl) {
-            const int buf = tl & 1, jt = tl % n_tiles;
-            const int row0 = ((int)blockIdx.x + (tl / n_tiles) * (int)gridDim.x) * LT_BM + q * 32;   // first row of this warp
+            const int buf = tl & 1, jt = js + (tl % my_nt) * nsplit;
+            const int row0 = (vb + (tl / my_nt) * vgrid) * LT_BM + q * 32;                             // first row of this warp
             mbar_wait(&tfull[buf], (uint32_t)((tl >> 1) & 1));
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256);
@@ -178,8 +181,13 @@ static int linear_launch_s(const void* A, const void* W, const float* bias, void
     const int smem = Cfg::SMEM;
     auto kern = linear_act_tc_kernel<BN, GELU, BF16, LT_STAGES>;
     XP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int64_t n_mb = ceil_div(M, LT_BM);
-    kern<<<(unsigned)(n_mb < num_sms() ? n_mb : num_sms()), LT_THREADS, smem, st>>>(ma, mw, bias, out, (int)M, (int)N, (int)K);
+    const int64_t n_mb = ceil_div(M, LT_BM), n_tiles = ceil_div(N, BN);
+    int64_t nsplit = 1, grid = num_sms();
+    if (n_mb < num_sms()) {                        // few row blocks (single-pair latency): spread the column tiles over the idle SMs
+        nsplit = std::max<int64_t>(1, std::min<int64_t>(n_tiles, num_sms() / n_mb));
+        grid = n_mb * nsplit;
+    }
+    kern<<<(unsigned)grid, LT_THREADS, smem, st>>>(ma, mw, bias, out, (int)M, (int)N, (int)K, (int)nsplit);
     XP_LAUNCH_CHECK("linear_act_tc_kernel");
     return XP_OK;
 }

@@ -306,6 +306,10 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 :: "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void tma_store_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory");
@@ -319,8 +323,9 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 
 // ------------------------------------------------------------------------------------ host: tensor maps
 // cuTensorMapEncodeTiled resolved through the runtime (no link-time dependency on libcuda).
-// dims/strides innermost-first; strides_bytes has rank-1 entries (dim 1..rank-1).  Returns XP_OK or error.
+// dims/strides innermost-first; strides_bytes has rank-1 entries (dim 1..rank-1).  swizzle: 0 none, 1 128B, 2 64B, 3 32B.
+// Returns XP_OK or error.
 int make_tensor_map(CUtensorMap* map, int dtype, int rank, const void* base, const uint64_t* dims,
-                    const uint64_t* strides_bytes, const uint32_t* box, int swizzle_128b);
+                    const uint64_t* strides_bytes, const uint32_t* box, int swizzle);
 
 }  // namespace xp

@@ -18,7 +18,8 @@
 //               16-bit -> H[g % 2] k-block in shared memory (fence.proxy.async before the GEMM2 issuer is told)
 //   warps 20-27 epilogue 2, thread = row, two warps (C/2-column halves) per lane quarter: acc2 + b2 + residual -> one-pass
 //               shifted sums -> x_new (fp32) and LayerNorm (16-bit) out.  The residual arrives by cp.async two 16-column units
-//               ahead (across tiles) in a per-warp ring whose slots double as the transpose buffers of the coalesced stores.
+//               ahead (across tiles) in a per-warp ring of TMA-swizzled slots; the new residual rows are written back in place
+//               and leave as one TMA store per unit (cp.async.bulk.tensor), the 16-bit rows likewise from two small slots.
 #include "common.cuh"
 #include "tcgen05.cuh"
 
@@ -31,10 +32,12 @@ constexpr int MP_E1G = MP_E1_WARPS / 2;                // warps per epilogue-1 g
 constexpr int MP_E1C = MP_HC / (MP_E1G / 4);           // hidden columns per epilogue-1 warp and chunk (32)
 constexpr int MP_THREADS = (4 + MP_E1_WARPS + MP_E2_WARPS) * 32;
 constexpr int MP_PF = 2;                               // residual units in flight per epilogue-2 warp
-constexpr int MP_STG_PITCH = 80, MP_STG = 32 * MP_STG_PITCH;      // 32 rows x (64 B + 16 B pad): one fp32 unit
-constexpr int MP_YSTG_PITCH = 48, MP_YSTG = 32 * MP_YSTG_PITCH;   // 32 rows x (32 B + 16 B pad): one 16-bit unit
-constexpr int MP_E2_SMEM = MP_PF * MP_STG + MP_YSTG;
-constexpr int MP_BAR_BYTES = 512;
+// epilogue-2 staging, all of it in the layouts TMA stores read: a ring of three fp32 units [32 rows x 64 B] (64B swizzle: 16-byte
+// piece ^= (row >> 1) & 3 -- conflict-free for thread = row) and two 16-bit units [32 rows x 32 B] (32B swizzle: piece ^= (row >> 2) & 1)
+constexpr int MP_XSLOT = 32 * 64, MP_XSLOTS = MP_PF + 1, MP_YSLOT = 32 * 32;
+constexpr int MP_E2_SMEM = MP_XSLOTS * MP_XSLOT + 2 * MP_YSLOT;
+static_assert(MP_E2_SMEM % 1024 == 0, "the swizzle patterns are functions of the absolute shared-memory address");
+constexpr int MP_BAR_BYTES = 256;
 
 template <int C> struct MpCfg {
     static constexpr int HD = 4 * C;
@@ -81,7 +84,8 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 template <int C, bool BF16>
 __global__ void __launch_bounds__(MP_THREADS, 1)
 mlp_res_ln_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w1,
-                     const __grid_constant__ CUtensorMap map_w2, const float* __restrict__ b1, const float* __restrict__ b2,
+                     const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_x,
+                     const __grid_constant__ CUtensorMap map_y, const float* __restrict__ b1, const float* __restrict__ b2,
                      const float* __restrict__ res, const float* __restrict__ gamma, const float* __restrict__ beta,
                      float* __restrict__ xnew, void* __restrict__ yout, int M, float eps) {
     using Cfg = MpCfg<C>;
@@ -92,7 +96,8 @@ mlp_res_ln_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     uint8_t* w1 = a1 + NA1 * Cfg::A1_BYTES;
     uint8_t* hbuf = w1 + S1 * Cfg::W1_STAGE;
     uint8_t* w2 = hbuf + Cfg::H_SMEM;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(w2 + S2 * Cfg::W2_STAGE);
+    uint8_t* e2_smem = w2 + S2 * Cfg::W2_STAGE;                                     // 1024-aligned: every tile above is n x 1 KiB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(e2_smem + MP_E2_WARPS * MP_E2_SMEM);
     uint64_t* a1_full = bars;                   // [NA1]
     uint64_t* a1_empty = a1_full + NA1;         // [NA1]
     uint64_t* w1_full = a1_empty + NA1;         // [S1]
@@ -106,8 +111,7 @@ mlp_res_ln_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     uint64_t* acc2_full = h_empty + 2;
     uint64_t* acc2_empty = acc2_full + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc2_empty + 2);
-    uint8_t* e2_smem = reinterpret_cast<uint8_t*>(bars) + MP_BAR_BYTES;
-    float* vec_s = reinterpret_cast<float*>(e2_smem + MP_E2_WARPS * MP_E2_SMEM);   // b1 [HD] | b2 [C] | gamma [C] | beta [C]
+    float* vec_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + MP_BAR_BYTES);   // b1 [HD] | b2 [C] | gamma [C] | beta [C]
     float2* sums_s = reinterpret_cast<float2*>(vec_s + Cfg::VEC_FLOATS);           // [2][MP_E2_WARPS][32]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -299,26 +303,31 @@ mlp_res_ln_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     } else if (warp >= 4 + MP_E1_WARPS) {
         // ===================== epilogue 2: + b2 + residual -> x_new, LayerNorm =====================
         const int e = warp - 4 - MP_E1_WARPS, q = e & 3, half = e >> 2;                // (warp % 4) == q
-        const uint32_t ring_s = smem_u32(e2_smem + e * MP_E2_SMEM), ystg_s = ring_s + MP_PF * MP_STG;
+        const uint32_t ring_s = smem_u32(e2_smem + e * MP_E2_SMEM), ys_s = ring_s + MP_XSLOTS * MP_XSLOT;
         const uint32_t sums_ss = smem_u32(sums_s);
         const uint32_t lane_t = (uint32_t)(q * 32) << 16;
         const int lr = lane >> 2, lp = lane & 3;
+        const uint32_t own64 = (uint32_t)(lane * 64), sw64 = (uint32_t)((lane >> 1) & 3);   // this thread's row of an fp32 unit
+        const uint32_t own32 = (uint32_t)(lane * 32), sw32 = (uint32_t)((lane >> 2) & 1);   //                  of a 16-bit unit
         const float invC = 1.0f / (float)C;
         const int nunits = ntl * UPW;
+        uint32_t ycount = 0;
         auto row0_of = [&](int tl) { return ((int)blockIdx.x + tl * (int)gridDim.x) * MP_BM + q * 32; };
-        auto prefetch = [&](int n) {                                                   // residual unit n -> ring slot n % PF
+        auto prefetch = [&](int n) {                                                   // residual unit n -> ring slot n % 3
             if (n < nunits) {
                 const int r0 = row0_of(n / UPW), col = half * (C / 2) + (n % UPW) * 16 + lp * 4;
-                const uint32_t dst = ring_s + (uint32_t)((n % MP_PF) * MP_STG + lp * 16);
+                const uint32_t dst = ring_s + (uint32_t)((n % MP_XSLOTS) * MP_XSLOT);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int r = lr + 8 * i;
                     const bool ok = r0 + r < M;
-                    cp_async16(dst + r * MP_STG_PITCH, res + (int64_t)(ok ? r0 + r : 0) * C + col, ok ? 16u : 0u);
+                    cp_async16(dst + (uint32_t)(r * 64) + (((uint32_t)lp ^ (uint32_t)((r >> 1) & 3)) << 4),
+                               res + (int64_t)(ok ? r0 + r : 0) * C + col, ok ? 16u : 0u);
                 }
             }
             cp_async_commit();
         };
+        if (lane == 0) { tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_y); }
 #pragma unroll
         for (int n = 0; n < MP_PF; ++n) prefetch(n);
 #pragma unroll 1
@@ -333,7 +342,7 @@ mlp_res_ln_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 #pragma unroll 1
             for (int k = 0; k < UPW; ++k) {
                 const int n = tl * UPW + k;
-                const uint32_t slot_s = ring_s + (uint32_t)((n % MP_PF) * MP_STG);
+                const uint32_t slot_s = ring_s + (uint32_t)((n % MP_XSLOTS) * MP_XSLOT);
                 const int col0 = half * (C / 2) + k * 16;
                 float v[16];
                 tmem_ld16(taddr + (uint32_t)(k * 16), v);
@@ -341,7 +350,7 @@ mlp_res_ln_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 __syncwarp();
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
-                    const uint4 rr = lds128(slot_s + lane * MP_STG_PITCH + jj * 16);
+                    const uint4 rr = lds128(slot_s + own64 + (((uint32_t)jj ^ sw64) << 4));
                     const float4 bb = lds_f4(vec_ss + (uint32_t)((Cfg::HD + col0 + 4 * jj) * 4));
                     v[4 * jj] += __uint_as_float(rr.x) + bb.x; v[4 * jj + 1] += __uint_as_float(rr.y) + bb.y;
                     v[4 * jj + 2] += __uint_as_float(rr.z) + bb.z; v[4 * jj + 3] += __uint_as_float(rr.w) + bb.w;
@@ -349,19 +358,17 @@ mlp_res_ln_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 #pragma unroll
                 for (int jj = 0; jj < 16; ++jj) { const float d = v[jj] - shift; s1 += d; s2 = fmaf(d, d, s2); }
                 tmem_st16(taddr + (uint32_t)(k * 16), v);
-                if (xnew) {
+                if (xnew) {                                // the new residual rows leave from the slot they arrived in: one TMA store
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj)
-                        sts128(slot_s + lane * MP_STG_PITCH + jj * 16, __float_as_uint(v[4 * jj]), __float_as_uint(v[4 * jj + 1]),
+                        sts128(slot_s + own64 + (((uint32_t)jj ^ sw64) << 4), __float_as_uint(v[4 * jj]), __float_as_uint(v[4 * jj + 1]),
                                __float_as_uint(v[4 * jj + 2]), __float_as_uint(v[4 * jj + 3]));
+                    fence_proxy_async();
                     __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int r = lr + 8 * i;
-                        const float4 val = lds_f4(slot_s + r * MP_STG_PITCH + lp * 16);
-                        if (row0 + r < M) *reinterpret_cast<float4*>(xnew + (int64_t)(row0 + r) * C + col0 + lp * 4) = val;
-                    }
+                    if (lane == 0) { tma_store_2d(&map_x, slot_s, col0, row0); tma_store_commit(); }
                 }
+                // the slot the next prefetch lands in held unit n - 1: its store is older than the one just committed
+                if (lane == 0) tma_store_wait_read<1>();
                 __syncwarp();
                 prefetch(n + MP_PF);
             }
@@ -375,8 +382,9 @@ mlp_res_ln_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             const float mean = gamma ? shift + m1 : 0.0f;
             const float rstd = gamma ? rsqrtf(fmaxf(fmaf(s2 + o.y, invC, -m1 * m1), 0.0f) + eps) : 1.0f;
 #pragma unroll 1
-            for (int k = 0; k < UPW; ++k) {
+            for (int k = 0; k < UPW; ++k, ++ycount) {
                 const int col0 = half * (C / 2) + k * 16;
+                const uint32_t yslot = ys_s + (ycount & 1u) * MP_YSLOT;
                 float v[16];
                 tmem_ld16(taddr + (uint32_t)(k * 16), v);
                 uint32_t pk[8];
@@ -394,23 +402,20 @@ mlp_res_ln_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                         pk[t / 2] = *reinterpret_cast<const uint32_t*>(&h0); pk[t / 2 + 1] = *reinterpret_cast<const uint32_t*>(&h1);
                     }
                 }
-                sts128(ystg_s + lane * MP_YSTG_PITCH, pk[0], pk[1], pk[2], pk[3]);
-                sts128(ystg_s + lane * MP_YSTG_PITCH + 16, pk[4], pk[5], pk[6], pk[7]);
+                if (lane == 0) tma_store_wait_read<1>();   // the store that last read this slot is two groups back
                 __syncwarp();
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const int r = (lane >> 1) + 16 * i, piece = lane & 1;
-                    const uint4 val = lds128(ystg_s + r * MP_YSTG_PITCH + piece * 16);
-                    if (row0 + r < M)
-                        *reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(yout) + (int64_t)(row0 + r) * C + col0 + piece * 8) = val;
-                }
+                sts128(yslot + own32 + ((0u ^ sw32) << 4), pk[0], pk[1], pk[2], pk[3]);
+                sts128(yslot + own32 + ((1u ^ sw32) << 4), pk[4], pk[5], pk[6], pk[7]);
+                fence_proxy_async();
                 __syncwarp();
+                if (lane == 0) { tma_store_2d(&map_y, yslot, col0, row0); tma_store_commit(); }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc2_empty[ab]);
         }
         cp_async_wait<0>();
+        if (lane == 0) tma_store_wait<0>();
     }
     tc_fence_before();
     __syncthreads();
@@ -440,11 +445,22 @@ static int mlp_launch(const void* A, const void* W1, const float* b1, const void
         const uint32_t box[2] = {MP_BK, (uint32_t)C};
         if ((rc = make_tensor_map(&mw2, dt, 2, W2, dims, strides, box, 1))) return rc;
     }
+    CUtensorMap mx, my;
+    {
+        const uint64_t dims[2] = {(uint64_t)C, (uint64_t)M}, strides[1] = {(uint64_t)C * 2};             // y (M, C) 16-bit
+        const uint32_t box[2] = {16, 32};
+        if ((rc = make_tensor_map(&my, dt, 2, y, dims, strides, box, 3))) return rc;
+        mx = my;
+        if (xnew) {
+            const uint64_t xstrides[1] = {(uint64_t)C * 4};                                               // x_new (M, C) fp32
+            if ((rc = make_tensor_map(&mx, XP_F32, 2, xnew, dims, xstrides, box, 2))) return rc;
+        }
+    }
     auto kern = mlp_res_ln_tc_kernel<C, BF16>;
     XP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     const int64_t n_mb = ceil_div(M, MP_BM);
-    kern<<<(unsigned)(n_mb < num_sms() ? n_mb : num_sms()), MP_THREADS, Cfg::SMEM, st>>>(ma, mw1, mw2, b1, b2, res, gamma, beta, xnew, y,
-                                                                                        (int)M, eps);
+    kern<<<(unsigned)(n_mb < num_sms() ? n_mb : num_sms()), MP_THREADS, Cfg::SMEM, st>>>(ma, mw1, mw2, mx, my, b1, b2, res, gamma, beta,
+                                                                                        xnew, y, (int)M, eps);
     XP_LAUNCH_CHECK("mlp_res_ln_tc_kernel");
     return XP_OK;
 }

@@ -35,7 +35,7 @@ int num_sms() {
 }
 
 int make_tensor_map(CUtensorMap* map, int dtype, int rank, const void* base, const uint64_t* dims,
-                    const uint64_t* strides_bytes, const uint32_t* box, int swizzle_128b) {
+                    const uint64_t* strides_bytes, const uint32_t* box, int swizzle) {
     static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
@@ -56,7 +56,8 @@ int make_tensor_map(CUtensorMap* map, int dtype, int rank, const void* base, con
     for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
     const CUresult r = encode(map, dt, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE,
-                              swizzle_128b ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                              swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_64B
+                              : swizzle == 3 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu x %llu, box %u x %u)", (int)r, rank,

@@ -11,4 +11,4 @@ timeout 1100 $SAN --tool memcheck python -m pytest tests -m gpu -q -x -k "$SEL_M
 echo "memcheck rc=$?" >> gpurun_out/r2_memcheck.log
 timeout 900 $SAN --tool racecheck python -m pytest tests -m gpu -q -x -k "$SEL_RACE" -p no:cacheprovider > gpurun_out/r2_racecheck.log 2>&1
 echo "racecheck rc=$?" >> gpurun_out/r2_racecheck.log
-tail -5 gpurun_out/r2_memcheck.log gpurun_out/r2_racecheck.log
+tail -n 5 gpurun_out/r2_memcheck.log; tail -n 5 gpurun_out/r2_racecheck.log

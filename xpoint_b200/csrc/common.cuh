@@ -176,6 +176,24 @@ __device__ __forceinline__ float softplus_f(float x) {
     return x > 20.0f ? x : r;
 }
 
+// The same function with ONE MUFU, for kernels that are bound by the XU pipe (the N >= 4 scan spends 16 ex2 per token and row on
+// its decay factors; softplus's ex2 + lg2 were another 11 % of that pipe):  softplus(x) = max(x, 0) + log1p(t), t = e^-|x| in (0, 1],
+// log1p(t) = t * Q(t) with Q the degree-8 minimax polynomial of log1p(t) / t on [0, 1] (max relative error 2.0e-7 evaluated in
+// fp32, i.e. the small-delta regime keeps fp32 accuracy; for x > 20 the correction is below half an ulp of x, so the result is x
+// exactly as torch's threshold branch returns it).
+__device__ __forceinline__ float softplus1_f(float x) {
+    const float t = ex2_approx(-fabsf(x) * kLog2e);
+    float q = fmaf(t, 0.005253457929939032f, -0.02958850748836994f);
+    q = fmaf(q, t, 0.07836166769266129f);
+    q = fmaf(q, t, -0.13674770295619965f);
+    q = fmaf(q, t, 0.19111430644989014f);
+    q = fmaf(q, t, -0.24844369292259216f);
+    q = fmaf(q, t, 0.33319270610809326f);
+    q = fmaf(q, t, -0.49999502301216125f);
+    q = fmaf(q, t, 1.0f);
+    return fmaf(q, t, fmaxf(x, 0.0f));
+}
+
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
 // exact (erf) GELU: erfc(x) = (1 + a1 x + .. + a6 x^6)^-16, x >= 0 (Abramowitz-Stegun 7.1.28, |err| <= 3e-7), evaluated in |v|

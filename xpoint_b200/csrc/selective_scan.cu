@@ -734,7 +734,7 @@ __device__ __forceinline__ void rows_consumer(const ScanParams& p, uint32_t sbas
             for (int j = 0; j < 4; ++j) {
                 const float uo = hf ? u8[2 * j + 1] : u8[2 * j];
                 const float x = (hf ? d8[2 * j + 1] : d8[2 * j]) + bias;
-                const float dlo = SOFTPLUS ? softplus_f(x) : x;
+                const float dlo = SOFTPLUS ? softplus1_f(x) : x;      // one MUFU: this kernel is bound by the XU pipe
                 const float duo = dlo * uo;
                 dl2[j] = make_float2(__shfl_sync(0xffffffffu, dlo, src0), __shfl_sync(0xffffffffu, dlo, src1));
                 du2[j] = make_float2(__shfl_sync(0xffffffffu, duo, src0), __shfl_sync(0xffffffffu, duo, src1));

@@ -3,8 +3,9 @@
 //     x_new = x + fc2( GELU( fc1(n) + b1 ) ) + b2 ;   y = LayerNorm_next(x_new)            (VMamba.py:110-128, 1229-1233)
 //
 // The 4C-wide hidden tensor (2 + 2 GB of HBM traffic per stage-0 block when fc1 and fc2 are separate kernels) never leaves
-// the SM: per 128-row tile the hidden activation is produced 64 columns at a time, GELU'd on its way out of TMEM, written to
-// shared memory as one K-major 128B-swizzled k-block of the second GEMM's A operand (double-buffered), and consumed there.
+// the SM: per 128-row tile the hidden activation is produced 64 columns at a time, GELU'd on its way out of TMEM and handed to the
+// second GEMM as its A operand (double-buffered) -- in tensor memory at C = 96 (packed 16-bit pairs, tcgen05.mma [d], [a_tmem], b),
+// as a K-major 128B-swizzled shared-memory k-block at C = 192, where the 512 TMEM columns are taken by the accumulators.
 //
 // Persistent CTAs over 128-row tiles, C = 96 or 192; 28 warps, each role with its own instruction stream so that the
 // FMA-pipe-bound GELU and the latency-bound residual / LayerNorm epilogue overlap.  g = flat index of a 64-column hidden chunk:
@@ -12,10 +13,10 @@
 //   warp 1      GEMM1 issuer (one lane): acc1[g % 2] = n W1[g]^T (K = C), as soon as its epilogue-1 group has read chunk g - 2
 //   warp 3      GEMM2 issuer (one lane): acc2[tile % 2] += H(g) W2[:, g]^T (K = 64) when H(g) is written.  Two issuers, because
 //               one thread issuing both GEMMs (with ring arithmetic) was the critical path of the whole CTA
-//   warp 2      TMEM allocation: acc1 2 x 64 columns + acc2 2 x C columns (512 at C = 192)
+//   warp 2      TMEM allocation: acc1 2 x 64 columns + acc2 2 x C columns (512 at C = 192) [+ H 2 x 32 columns at C = 96]
 //   warps 4-19  epilogue 1, thread = row: two groups of 8 warps (even / odd chunks, so one group's barrier waits hide behind the
 //               other's arithmetic), two warps (32-column halves) per TMEM lane quarter: tcgen05.ld -> + b1 -> exact GELU ->
-//               16-bit -> H[g % 2] k-block in shared memory (fence.proxy.async before the GEMM2 issuer is told)
+//               16-bit -> H[g % 2]: tcgen05.st into tensor memory, or the shared-memory k-block (+ fence.proxy.async) at C = 192
 //   warps 20-27 epilogue 2, thread = row, two warps (C/2-column halves) per lane quarter: acc2 + b2 + residual -> one-pass
 //               shifted sums -> x_new (fp32) and LayerNorm (16-bit) out.  The residual arrives by cp.async two 16-column units
 //               ahead (across tiles) in a per-warp ring of TMA-swizzled slots; the new residual rows are written back in place
